@@ -1,0 +1,20 @@
+import logging as _logging
+
+USE_PEFT_BACKEND = False
+
+
+class _Logging:
+    @staticmethod
+    def get_logger(name):
+        return _logging.getLogger(name)
+
+
+logging = _Logging()
+
+
+def scale_lora_layers(model, weight):
+    return None
+
+
+def unscale_lora_layers(model, weight=None):
+    return None
