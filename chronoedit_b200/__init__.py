@@ -1,0 +1,12 @@
+"""chronoedit_b200 — B200-native (sm_100a) implementation of the ChronoEdit denoising hot path.
+
+Public surface (drop-in for the objects `ChronoEditPipeline` registers, pipeline_chronoedit.py:175-183):
+  ChronoEditTransformer3DModel   <- chronoedit_diffusers/transformer_chronoedit.py:298-476
+  AutoencoderKLWan               <- diffusers AutoencoderKLWan (arithmetic twin: chronoedit/_src/tokenizers/wan2pt1.py)
+Both call hand-written CUDA kernels in lib/libchronoedit_b200.so through the C ABI of include/chronoedit_b200.h.
+Importing this package does not need a GPU; running anything does (there is no CPU fallback).
+"""
+from ._lib import CEError, LIB_PATH, lib  # noqa: F401
+from .transformer import ChronoEditTransformer3DModel, Transformer2DModelOutput  # noqa: F401
+
+__all__ = ["ChronoEditTransformer3DModel", "Transformer2DModelOutput", "CEError", "lib", "LIB_PATH"]

@@ -1,0 +1,316 @@
+// Non-causal multi-head attention forward for sm_100a (head_dim 128), flash-style, on tcgen05.
+//
+//   out[b, i, h*128:(h+1)*128] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) @ v[b,j,h,:]
+//
+// One CTA per (128-query tile, head, batch); 320 threads:
+//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (128 keys) through 2-deep rings
+//   warp 1      MMA issuer:   S_j = Q K_j^T  (M128 N128 K128, accumulator S_{j&1} in TMEM)
+//                             O_{j&1} += P_j V_j (P_j from shared memory, V_j as MN-major B operand)
+//   warps 2-5   softmax group 0 (even key tiles), warps 6-9 softmax group 1 (odd key tiles):
+//               TMEM -> registers, running max / sum (fp32), exp2, bf16 P -> shared memory (128B-swizzled A tile)
+// The two groups keep INDEPENDENT online-softmax streams (own max, sum and O accumulator) that are merged once
+// at the end, so S_{j+1} and softmax_j / PV_j overlap without any cross-group exchange in the loop.
+// O is rescaled lazily: only when the row max grows by more than 2^8 (values stay bounded, result identical
+// after the final normalisation).
+//
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+// Shared memory: Q 32K | K 2x32K | V 2x32K | P 2x32K | barriers.
+//
+// Replaces F.scaled_dot_product_attention at /root/reference/chronoedit_diffusers/transformer_chronoedit.py:91-99
+// (self-attention, text cross-attention and image cross-attention; the latter two are summed, :103-104).
+#include "attention.cuh"
+
+namespace ce {
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int ATTN_THREADS = 320;
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 16 KB [128 x 64] swizzled blocks
+constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
+constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
+
+struct SmemLayout {
+  static constexpr uint32_t q = 0;
+  static constexpr uint32_t k = q + TILE_BYTES;
+  static constexpr uint32_t v = k + 2 * TILE_BYTES;
+  static constexpr uint32_t p = v + 2 * TILE_BYTES;
+  static constexpr uint32_t bars = p + 2 * TILE_BYTES;
+  static constexpr uint32_t total = bars + 256;
+};
+
+// barrier indices
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, PV_DONE = 13, NUM_BARS = 15 };
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                     const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (a.Lk + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[chronoedit_b200] attention: dynamic shared memory not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(&bars[i], (i == P_FULL || i == P_FULL + 1) ? 128 : 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[Q_FULL], TILE_BYTES);
+      tma_load_3d(smem + SmemLayout::q, &tma_q, &bars[Q_FULL], h * HD, q0, b);
+      tma_load_3d(smem + SmemLayout::q + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        uint8_t* ks = smem + SmemLayout::k + st * TILE_BYTES;
+        uint8_t* vs = smem + SmemLayout::v + st * TILE_BYTES;
+        mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 10 + st);
+        mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
+        tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, j * BKV, b);
+        tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, j * BKV, b);
+        mbar_wait(&bars[V_EMPTY + st], ph ^ 1, 20 + st);
+        mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
+        tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, j * BKV, b);
+        tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major) x K^T (K-major)
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (K-major) x V (MN-major)
+      const uint32_t q_addr = smem_u32(smem + SmemLayout::q);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 30 + st);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + SmemLayout::k + st * TILE_BYTES);
+        const uint32_t d = tmem_base + (j & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * HALF_BYTES;
+          umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3),
+                       umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S, kk != 0);
+        }
+        umma_commit(&bars[K_EMPTY + st]);
+        umma_commit(&bars[S_FULL + (j & 1)]);
+      };
+      mbar_wait(&bars[Q_FULL], 0, 1);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        const int g = j & 1;
+        const int t = j >> 1;
+        mbar_wait(&bars[P_FULL + g], t & 1, 40 + g);
+        mbar_wait(&bars[V_FULL + g], t & 1, 50 + g);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
+        const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
+        const uint32_t d = tmem_base + 256 + g * 128;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
+          umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
+        }
+        umma_commit(&bars[V_EMPTY + g]);
+        umma_commit(&bars[PV_DONE + g]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax groups
+    const int g = (warp - 2) >> 2;       // 0: even key tiles, 1: odd key tiles
+    const int quad = warp & 3;           // TMEM lane quadrant of this warp
+    const int r = quad * 32 + lane;      // query row inside the tile
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base + g * 128;
+    const uint32_t o_tmem = tmem_base + lane_base + 256 + g * 128;
+    uint8_t* p_smem = smem + SmemLayout::p + g * TILE_BYTES;
+    const float sl2 = a.scale * 1.4426950408889634f;
+    const int my_tiles = (n_tiles - g + 1) / 2;
+    float m = -INFINITY, l = 0.f;
+
+    for (int t = 0; t < my_tiles; ++t) {
+      const int j = 2 * t + g;
+      const int valid = a.Lk - j * BKV;  // >= 1; >= 128 means no masking
+      mbar_wait(&bars[S_FULL + g], t & 1, 60 + g);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld_32x32(s_tmem + c * 32, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = __uint_as_float(s[i]);
+          mx = (c * 32 + i < valid) ? fmaxf(mx, x) : mx;
+        }
+      }
+      mx *= sl2;
+      if (t == 0) {
+        m = mx;
+      } else {
+        mbar_wait(&bars[PV_DONE + g], (t - 1) & 1, 70 + g);  // previous P@V of this group done: O stable, P buffer free
+        tc_fence_after();
+        const bool need = mx > m + RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m - mx) : 1.0f;
+          if (need) m = mx;
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_tmem + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_tmem + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: p = exp2(s*scale*log2e - m) -> bf16 -> shared memory (K-major, 128B swizzle: chunk ^= row & 7)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld_32x32(s_tmem + c * 32, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(__uint_as_float(s[2 * i]) * sl2 - m);
+          float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) * sl2 - m);
+          p0 = (c * 32 + 2 * i < valid) ? p0 : 0.f;
+          p1 = (c * 32 + 2 * i + 1 < valid) ? p1 : 0.f;
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* row_base = p_smem + (c >> 1) * HALF_BYTES + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
+          *reinterpret_cast<uint4*>(row_base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      l += lsum;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[P_FULL + g]);
+    }
+
+    // ---- merge the two streams and write the output tile
+    if (my_tiles > 0) {
+      mbar_wait(&bars[PV_DONE + g], (my_tiles - 1) & 1, 80 + g);
+      tc_fence_after();
+    }
+    float2* xch = reinterpret_cast<float2*>(p_smem);  // own P buffer is free now
+    xch[r] = make_float2(m, l);
+    tc_fence_before();
+    named_bar_sync(1, 256);
+    tc_fence_after();
+    const float2 other = reinterpret_cast<const float2*>(smem + SmemLayout::p + (g ^ 1) * TILE_BYTES)[r];
+    const float m_e = g == 0 ? m : other.x, l_e = g == 0 ? l : other.y;
+    const float m_o = g == 0 ? other.x : m, l_o = g == 0 ? other.y : l;
+    const bool has_o = n_tiles > 1;
+    const float mm = has_o ? fmaxf(m_e, m_o) : m_e;
+    const float a_e = fast_exp2(m_e - mm);
+    const float a_o = has_o ? fast_exp2(m_o - mm) : 0.f;
+    const float inv = 1.0f / (l_e * a_e + l_o * a_o);
+    const float w_e = a_e * inv, w_o = a_o * inv;
+    const int row = q0 + r;
+    bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD + g * 64;
+    const uint32_t oe_tmem = tmem_base + lane_base + 256 + g * 64;
+    const uint32_t oo_tmem = tmem_base + lane_base + 384 + g * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t oe[32], oo[32];
+      tmem_ld_32x32(oe_tmem + c * 32, oe);
+      if (has_o) tmem_ld_32x32(oo_tmem + c * 32, oo);
+      tmem_ld_wait();
+      if (row < a.Lq) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            y[i] = __uint_as_float(oe[v4 * 8 + i]) * w_e;
+            if (has_o) y[i] += __uint_as_float(oo[v4 * 8 + i]) * w_o;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8);
+          if (a.accumulate) {
+            const uint4 pv = *dst;
+            const float2 p0 = unpack_bf16x2(pv.x), p1 = unpack_bf16x2(pv.y), p2 = unpack_bf16x2(pv.z),
+                         p3 = unpack_bf16x2(pv.w);
+            const float prev[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = bf16_round(y[i]) + prev[i];
+          }
+          *dst = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                            pack_bf16x2(y[6], y[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld) {
+  uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+}  // namespace
+
+int launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
+  CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
+  CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
+  CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_qkv_tmap(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
+  if ((rc = make_qkv_tmap(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
+  if ((rc = make_qkv_tmap(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SmemLayout::total));
+    attr_set = true;
+  }
+  dim3 grid((a.Lq + BQ - 1) / BQ, a.H, a.B);
+  attention_fwd_kernel<<<grid, ATTN_THREADS, SmemLayout::total, stream>>>(tq, tk, tv, a);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+}  // namespace ce

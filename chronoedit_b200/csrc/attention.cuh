@@ -1,0 +1,24 @@
+// Interface of the tcgen05 attention forward (attention.cu).
+#pragma once
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ce {
+
+struct AttnArgs {
+  int B = 0, H = 0, Lq = 0, Lk = 0, head_dim = 128;
+  const bf16* q = nullptr;  // q[b, i, h*hd + d] at q + (b*Lq + i)*ldq + h*hd + d
+  int ldq = 0;
+  const bf16* k = nullptr;  // k[b, j, h*hd + d] at k + (b*Lk + j)*ldk + ...
+  int ldk = 0;
+  const bf16* v = nullptr;
+  int ldv = 0;
+  bf16* out = nullptr;      // out[b, i, h*hd + d]
+  int ldo = 0;
+  float scale = 0.f;        // 1/sqrt(head_dim)
+  int accumulate = 0;       // 1: out = bf16(float(bf16(attn)) + float(out))   (image + text cross-attention sum)
+};
+
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+}  // namespace ce

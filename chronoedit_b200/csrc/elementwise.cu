@@ -1,0 +1,330 @@
+// HBM-bound row kernels of the DiT path: fp32 LayerNorm + adaLN modulate, RMSNorm-across-heads + 3D RoPE,
+// patchify / unpatchify, and the tiny-M Linear layers of the time embedder.  All are coalesced 16-byte
+// accesses with one CTA per token row (rows >> SM count), statistics in fp32 via warp shuffles.
+#include "elementwise.cuh"
+
+namespace ce {
+
+namespace {
+
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_VEC_PER_THREAD = 4;  // 8 bf16 per vector -> D <= 256*4*8 = 8192
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect `red` against the previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int D, float eps,
+                 const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
+                 const float* __restrict__ weight, const float* __restrict__ bias) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
+  float v[MAX_VEC_PER_THREAD][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
+    const int idx = threadIdx.x + i * ROW_THREADS;
+    if (idx < nvec) {
+      unpack8(xr[idx], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = block_sum(s, red) / (float)D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
+    const int idx = threadIdx.x + i * ROW_THREADS;
+    if (idx < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / (float)D + eps);
+  const int b = row / rows_per_batch;
+  uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
+    const int idx = threadIdx.x + i * ROW_THREADS;
+    if (idx < nvec) {
+      float o[8];
+      const int c = idx * 8;
+      if (scale) {
+        const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c);
+        const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride + c);
+        const float4 s0 = sc[0], s1 = sc[1], h0 = sh[0], h1 = sh[1];
+        const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + scv[j]) + shv[j];
+      } else if (weight) {
+        const float4* wp = reinterpret_cast<const float4*>(weight + c);
+        const float4* bp = reinterpret_cast<const float4*>(bias + c);
+        const float4 w0 = wp[0], w1 = wp[1], b0 = bp[0], b1 = bp[1];
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+      }
+      yr[idx] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int D, float eps, const bf16* __restrict__ weight,
+                    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
+  const uint4* wr = reinterpret_cast<const uint4*>(weight);
+  float v[MAX_VEC_PER_THREAD][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
+    const int idx = threadIdx.x + i * ROW_THREADS;
+    if (idx < nvec) {
+      unpack8(xr[idx], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+    }
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / (float)D + eps);
+  const int tok = rope_cos ? row % L : 0;
+  const int half = head_dim >> 1;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
+    const int idx = threadIdx.x + i * ROW_THREADS;
+    if (idx < nvec) {
+      float w[8], o[8];
+      unpack8(wr[idx], w);
+      // diffusers RMSNorm with a bf16 weight: (x * rstd) rounded to bf16, then * weight (bf16 multiply)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round(v[i][j] * rstd) * w[j]);
+      if (rope_cos) {
+        const int c = idx * 8;
+        const int pair0 = (c % head_dim) >> 1;  // 4 consecutive (even, odd) pairs of one head
+        const float4 cs = *reinterpret_cast<const float4*>(rope_cos + (size_t)tok * half + pair0);
+        const float4 sn = *reinterpret_cast<const float4*>(rope_sin + (size_t)tok * half + pair0);
+        const float cv[4] = {cs.x, cs.y, cs.z, cs.w};
+        const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float re = o[2 * p], im = o[2 * p + 1];
+          o[2 * p] = re * cv[p] - im * sv[p];
+          o[2 * p + 1] = re * sv[p] + im * cv[p];
+        }
+      }
+      xr[idx] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ patches, int B, int C, int T, int H, int W) {
+  const int hp = H >> 1, wp = W >> 1;
+  const int K = C * 4;
+  const size_t total = (size_t)B * T * hp * wp * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    size_t r = i / K;
+    const int j = (int)(r % wp); r /= wp;
+    const int ii = (int)(r % hp); r /= hp;
+    const int f = (int)(r % T);
+    const int b = (int)(r / T);
+    const int c = k >> 2, dh = (k >> 1) & 1, dw = k & 1;
+    patches[i] = x[((((size_t)b * C + c) * T + f) * H + (2 * ii + dh)) * W + (2 * j + dw)];
+  }
+}
+
+__global__ void unpatchify_kernel(const bf16* __restrict__ y, int ldy, bf16* __restrict__ out, int B, int C, int T, int H, int W) {
+  const int hp = H >> 1, wp = W >> 1;
+  const size_t total = (size_t)B * C * T * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int w = (int)(r % W); r /= W;
+    const int hh = (int)(r % H); r /= H;
+    const int f = (int)(r % T); r /= T;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const size_t row = (((size_t)b * T + f) * hp + (hh >> 1)) * wp + (w >> 1);
+    out[i] = y[row * ldy + ((hh & 1) * 2 + (w & 1)) * C + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int SL_MAX_B = 8;
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <bool W_BF16>
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, int K, const void* __restrict__ Wv, const void* __restrict__ biasv, int N,
+                    int B, int act, int in_silu_bf16, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float acc[SL_MAX_B];
+#pragma unroll
+  for (int b = 0; b < SL_MAX_B; ++b) acc[b] = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float w[4];
+    if (W_BF16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(Wv) + (size_t)warp * K + k);
+      const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+      w[0] = a.x; w[1] = a.y; w[2] = c.x; w[3] = c.y;
+    } else {
+      const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Wv) + (size_t)warp * K + k);
+      w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+    }
+#pragma unroll
+    for (int b = 0; b < SL_MAX_B; ++b) {
+      if (b < B) {
+        float4 xv = *reinterpret_cast<const float4*>(x + (size_t)b * K + k);
+        if (in_silu_bf16) {  // act_fn(temb) evaluated on the bf16 tensor: SiLU in fp32, rounded to bf16
+          xv.x = bf16_round(silu_f(xv.x)); xv.y = bf16_round(silu_f(xv.y));
+          xv.z = bf16_round(silu_f(xv.z)); xv.w = bf16_round(silu_f(xv.w));
+        }
+        acc[b] += xv.x * w[0] + xv.y * w[1] + xv.z * w[2] + xv.w * w[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < SL_MAX_B; ++b) acc[b] = warp_sum(acc[b]);
+  if (lane == 0) {
+    float bias = 0.f;
+    if (biasv) bias = W_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(biasv)[warp]) : reinterpret_cast<const float*>(biasv)[warp];
+    for (int b = 0; b < B; ++b) {
+      float y = acc[b] + bias;
+      if (out_bf16) y = bf16_round(y);  // the Linear output is a bf16 tensor in the reference
+      if (act == 1) y = silu_f(y);
+      if (out_f32) out_f32[(size_t)b * N + warp] = y;
+      if (out_bf16) out_bf16[(size_t)b * N + warp] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, float* __restrict__ emb, int B, int dim) {
+  const int half = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  // exponent = -ln(10000) * k / half (fp32, as torch.arange(float32) * scalar / half), freq = exp(exponent)
+  const float exponent = (-9.210340371976184f * (float)k) / (float)half;
+  const float arg = t[b] * expf(exponent);
+  emb[(size_t)b * dim + k] = cosf(arg);
+  emb[(size_t)b * dim + half + k] = sinf(arg);
+}
+
+__global__ void add_table_kernel(const float* __restrict__ table, int table_rows, const bf16* __restrict__ src, int src_ld,
+                                 int src_per_chunk, float* __restrict__ dst, int B, int n, int chunks) {
+  // dst[l, b, c, d] = table[l, c, d] + float(src[b, (src_per_chunk ? c*n : 0) + d])
+  const size_t total = (size_t)table_rows * B * chunks * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % n);
+    size_t r = i / n;
+    const int c = (int)(r % chunks); r /= chunks;
+    const int b = (int)(r % B);
+    const int l = (int)(r / B);
+    dst[i] = table[((size_t)l * chunks + c) * n + d] + __bfloat162float(src[(size_t)b * src_ld + (src_per_chunk ? c * n : 0) + d]);
+  }
+}
+
+}  // namespace
+
+int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
+                     const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
+                     cudaStream_t stream) {
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= ROW_THREADS * MAX_VEC_PER_THREAD * 8, "layernorm: D must be a multiple of 8 and <= 8192");
+  CE_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: leading dims % 8");
+  CE_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale and shift come together");
+  CE_REQUIRE((weight == nullptr) == (bias == nullptr), "layernorm: weight and bias come together");
+  if (rows_per_batch <= 0) rows_per_batch = rows;
+  layernorm_kernel<<<rows, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight, const float* rope_cos,
+                        const float* rope_sin, int L, int head_dim, cudaStream_t stream) {
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= ROW_THREADS * MAX_VEC_PER_THREAD * 8, "rmsnorm: D must be a multiple of 8 and <= 8192");
+  CE_REQUIRE(ldx % 8 == 0 && weight != nullptr, "rmsnorm: ldx % 8, weight");
+  if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm: rope table / head_dim");
+  rmsnorm_rope_kernel<<<rows, ROW_THREADS, 0, stream>>>(x, ldx, D, eps, weight, rope_cos, rope_sin, L, head_dim);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_patchify(const bf16* x, bf16* patches, int B, int C, int T, int H, int W, cudaStream_t stream) {
+  CE_REQUIRE(H % 2 == 0 && W % 2 == 0, "patchify: H, W must be even");
+  const size_t total = (size_t)B * T * (H / 2) * (W / 2) * C * 4;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  patchify_kernel<<<grid, 256, 0, stream>>>(x, patches, B, C, T, H, W);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_unpatchify(const bf16* y, int ldy, bf16* out, int B, int C, int T, int H, int W, cudaStream_t stream) {
+  const size_t total = (size_t)B * C * T * H * W;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  unpatchify_kernel<<<grid, 256, 0, stream>>>(y, ldy, out, B, C, T, H, W);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_small_linear(const float* x, int K, const void* W, const void* bias, int w_is_bf16, int N, int B, int act,
+                        int in_silu_bf16, float* out_f32, bf16* out_bf16, cudaStream_t stream) {
+  CE_REQUIRE(B >= 1 && B <= SL_MAX_B, "small_linear: batch must be 1..8");
+  CE_REQUIRE(K % 4 == 0, "small_linear: K % 4");
+  const int blocks = (N * 32 + 255) / 256;
+  if (w_is_bf16)
+    small_linear_kernel<true><<<blocks, 256, 0, stream>>>(x, K, W, bias, N, B, act, in_silu_bf16, out_f32, out_bf16);
+  else
+    small_linear_kernel<false><<<blocks, 256, 0, stream>>>(x, K, W, bias, N, B, act, in_silu_bf16, out_f32, out_bf16);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_timestep_sinusoid(const float* t, float* emb, int B, int dim, cudaStream_t stream) {
+  const int n = B * (dim / 2);
+  timestep_sinusoid_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, emb, B, dim);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_add_table(const float* table, int table_rows, const bf16* src, int src_ld, float* dst, int B, int n,
+                     int chunks, cudaStream_t stream) {
+  const size_t total = (size_t)table_rows * B * chunks * n;
+  const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int src_per_chunk = src_ld >= chunks * n ? 1 : 0;
+  add_table_kernel<<<grid, 256, 0, stream>>>(table, table_rows, src, src_ld, src_per_chunk, dst, B, n, chunks);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+}  // namespace ce

@@ -1,0 +1,41 @@
+// Interface of the HBM-bound row kernels of the DiT path (elementwise.cu).
+#pragma once
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ce {
+
+// y[row, :] = bf16( LN_fp32(x[row, :]) * (1 + scale[b, :]) + shift[b, :] )     (b = row / rows_per_batch)
+//   scale/shift: fp32 [batches, mod_stride] or null (then the optional affine weight/bias, fp32 [D], is applied)
+// FP32LayerNorm + adaLN modulate of transformer_chronoedit.py:279, 289, 460 and the affine norm2 of :284.
+int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
+                     const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
+                     cudaStream_t stream);
+
+// In place on x[rows, D] (leading dim ldx): diffusers RMSNorm across all heads (fp32 variance over D,
+// y = bf16(bf16(x * rstd) * w)), then optionally interleaved-pair RoPE with cos/sin tables [L, hd/2] fp32
+// (token = row % L).  transformer_chronoedit.py:62-65 and :71-79.
+int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight, const float* rope_cos,
+                        const float* rope_sin, int L, int head_dim, cudaStream_t stream);
+
+// patches[(b,f,i,j), c*4 + dh*2 + dw] = x[b, c, f, 2i+dh, 2j+dw]   (im2row for the k=s=(1,2,2) patch-embedding conv, :368,429-430)
+int launch_patchify(const bf16* x, bf16* patches, int B, int C, int T, int H, int W, cudaStream_t stream);
+// out[b, c, f, 2i+dh, 2j+dw] = y[(b,f,i,j), (dh*2+dw)*C + c]       (unpatchify permute of :463-467)
+int launch_unpatchify(const bf16* y, int ldy, bf16* out, int B, int C, int T, int H, int W, cudaStream_t stream);
+
+// out[b, n] = act( sum_k x[b,k] * W[n,k] + bias[n] );  tiny-M Linear (time embedder / time_proj, :155-159).
+//   w_is_bf16: weights/bias bf16 (else fp32); x is fp32; out fp32 (out_f32) and/or bf16 (out_bf16).
+//   in_silu_bf16: the input is first mapped through bf16(SiLU(x)) (act_fn applied to the bf16 temb tensor).
+//   act: 0 none, 1 SiLU on the output.  When out_bf16 is given the Linear result is rounded to bf16 first (and
+//   out_f32, if also given, receives that rounded value).
+int launch_small_linear(const float* x, int K, const void* W, const void* bias, int w_is_bf16, int N, int B,
+                        int act, int in_silu_bf16, float* out_f32, bf16* out_bf16, cudaStream_t stream);
+
+// emb[b, :] = [cos(t_b * f_i) | sin(t_b * f_i)], f_i = exp(-ln(10000) * i / half)   (diffusers Timesteps, flip_sin_to_cos)
+int launch_timestep_sinusoid(const float* t, float* emb, int B, int dim, cudaStream_t stream);
+
+// dst[b, :] = table[b % table_rows, :] + src[b, :] (fp32): scale_shift_table + temb (:274-276, :451)
+int launch_add_table(const float* table, int table_rows, const bf16* src, int src_ld, float* dst, int B, int n,
+                     int chunks, cudaStream_t stream);
+
+}  // namespace ce

@@ -1,0 +1,401 @@
+"""B200-native drop-in for `ChronoEditTransformer3DModel`.
+
+Host-side mirror of /root/reference/chronoedit_diffusers/transformer_chronoedit.py:298-476: same constructor
+arguments, same parameter names (so a diffusers checkpoint / `state_dict` loads unchanged), same
+`forward(hidden_states, timestep, encoder_hidden_states, encoder_hidden_states_image=None, return_dict=True,
+attention_kwargs=None)` signature and return types, `.config`, `.dtype`, `from_pretrained`.  All arithmetic happens in
+libchronoedit_b200.so (hand-written sm_100a kernels) through the C ABI of include/chronoedit_b200.h; PyTorch only
+owns the memory and the stream.  There is no PyTorch fallback path.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import CEError, DiTConfigC, check, current_stream, ptr
+
+# reference `_keep_in_fp32_modules` (transformer_chronoedit.py:338)
+KEEP_FP32 = ("time_embedder", "scale_shift_table", "norm1", "norm2", "norm3")
+
+
+@dataclass
+class Transformer2DModelOutput:
+    """Same shape as diffusers.models.modeling_outputs.Transformer2DModelOutput."""
+
+    sample: torch.Tensor
+
+
+class _Config(dict):
+    """Attribute + item access, like diffusers' FrozenDict config."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class _P(nn.Module):
+    """Parameter holder (weight[, bias]) — shapes/names follow the reference module tree; no forward."""
+
+    def __init__(self, weight_shape, bias_shape=None, dtype=torch.bfloat16, device=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(weight_shape, dtype=dtype, device=device), requires_grad=False)
+        if bias_shape is not None:
+            self.bias = nn.Parameter(torch.empty(bias_shape, dtype=dtype, device=device), requires_grad=False)
+
+
+class _GELU(nn.Module):
+    def __init__(self, din, dout, dtype, device):
+        super().__init__()
+        self.proj = _P((dout, din), (dout,), dtype, device)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, din, inner, dout, dtype, device):
+        super().__init__()
+        self.net = nn.ModuleList([_GELU(din, inner, dtype, device), nn.Identity(), _P((dout, inner), (dout,), dtype, device)])
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, added_kv_proj_dim, dtype, device):
+        super().__init__()
+        self.norm_q = _P((dim,), None, dtype, device)
+        self.norm_k = _P((dim,), None, dtype, device)
+        self.to_q = _P((dim, dim), (dim,), dtype, device)
+        self.to_k = _P((dim, dim), (dim,), dtype, device)
+        self.to_v = _P((dim, dim), (dim,), dtype, device)
+        if added_kv_proj_dim is not None:
+            self.add_k_proj = _P((dim, added_kv_proj_dim), (dim,), dtype, device)
+            self.add_v_proj = _P((dim, added_kv_proj_dim), (dim,), dtype, device)
+            self.norm_added_k = _P((dim,), None, dtype, device)
+        self.to_out = nn.ModuleList([_P((dim, dim), (dim,), dtype, device), nn.Identity()])
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, ffn_dim, added_kv_proj_dim, dtype, device):
+        super().__init__()
+        self.attn1 = _Attention(dim, None, dtype, device)
+        self.attn2 = _Attention(dim, added_kv_proj_dim, dtype, device)
+        self.norm2 = _P((dim,), (dim,), torch.float32, device)
+        self.ffn = _FeedForward(dim, ffn_dim, dim, dtype, device)
+        self.scale_shift_table = nn.Parameter(torch.empty(1, 6, dim, dtype=torch.float32, device=device), requires_grad=False)
+
+
+class _TimestepEmbedding(nn.Module):
+    def __init__(self, freq_dim, dim, device):
+        super().__init__()
+        self.linear_1 = _P((dim, freq_dim), (dim,), torch.float32, device)
+        self.linear_2 = _P((dim, dim), (dim,), torch.float32, device)
+
+
+class _TextProjection(nn.Module):
+    def __init__(self, din, dim, dtype, device):
+        super().__init__()
+        self.linear_1 = _P((dim, din), (dim,), dtype, device)
+        self.linear_2 = _P((dim, dim), (dim,), dtype, device)
+
+
+class _ImageEmbedding(nn.Module):
+    def __init__(self, din, dout, dtype, device):
+        super().__init__()
+        self.norm1 = _P((din,), (din,), torch.float32, device)
+        self.ff = _FeedForward(din, din, dout, dtype, device)
+        self.norm2 = _P((dout,), (dout,), torch.float32, device)
+
+
+class _ConditionEmbedder(nn.Module):
+    def __init__(self, dim, freq_dim, text_dim, image_dim, dtype, device):
+        super().__init__()
+        self.time_embedder = _TimestepEmbedding(freq_dim, dim, device)
+        self.time_proj = _P((6 * dim, dim), (6 * dim,), dtype, device)
+        self.text_embedder = _TextProjection(text_dim, dim, dtype, device)
+        if image_dim is not None:
+            self.image_embedder = _ImageEmbedding(image_dim, dim, dtype, device)
+
+
+class ChronoEditTransformer3DModel(nn.Module):
+    """See module docstring.  Constructor arguments = transformer_chronoedit.py:342-360."""
+
+    config_name = "config.json"
+
+    def __init__(
+        self,
+        patch_size: Tuple[int, int, int] = (1, 2, 2),
+        num_attention_heads: int = 40,
+        attention_head_dim: int = 128,
+        in_channels: int = 16,
+        out_channels: int = 16,
+        text_dim: int = 4096,
+        freq_dim: int = 256,
+        ffn_dim: int = 13824,
+        num_layers: int = 40,
+        cross_attn_norm: bool = True,
+        qk_norm: Optional[str] = "rms_norm_across_heads",
+        eps: float = 1e-6,
+        image_dim: Optional[int] = None,
+        added_kv_proj_dim: Optional[int] = None,
+        rope_max_seq_len: int = 1024,
+        rope_temporal_skip_len: int = 8,
+        *,
+        torch_dtype: torch.dtype = torch.bfloat16,
+        device: Optional[Union[str, torch.device]] = None,
+    ) -> None:
+        super().__init__()
+        if torch_dtype != torch.bfloat16:
+            raise CEError("chronoedit_b200 computes in bf16 (fp32 for the reference's _keep_in_fp32_modules); "
+                          f"torch_dtype={torch_dtype} is not built")
+        if tuple(patch_size) != (1, 2, 2) or attention_head_dim != 128:
+            raise CEError("only patch_size (1,2,2) and attention_head_dim 128 are built")
+        if not cross_attn_norm or qk_norm != "rms_norm_across_heads":
+            raise CEError("only cross_attn_norm=True, qk_norm='rms_norm_across_heads' (the ChronoEdit configuration) is built")
+        if (image_dim is None) != (added_kv_proj_dim is None):
+            raise CEError("image_dim and added_kv_proj_dim must be given together (I2V configuration)")
+        out_channels = out_channels or in_channels
+        self.config = _Config(
+            patch_size=tuple(patch_size), num_attention_heads=num_attention_heads, attention_head_dim=attention_head_dim,
+            in_channels=in_channels, out_channels=out_channels, text_dim=text_dim, freq_dim=freq_dim, ffn_dim=ffn_dim,
+            num_layers=num_layers, cross_attn_norm=cross_attn_norm, qk_norm=qk_norm, eps=eps, image_dim=image_dim,
+            added_kv_proj_dim=added_kv_proj_dim, rope_max_seq_len=rope_max_seq_len,
+            rope_temporal_skip_len=rope_temporal_skip_len)
+        dim = num_attention_heads * attention_head_dim
+        dt = torch_dtype
+        self.patch_embedding = _P((dim, in_channels) + tuple(patch_size), (dim,), dt, device)
+        self.condition_embedder = _ConditionEmbedder(dim, freq_dim, text_dim, image_dim, dt, device)
+        self.blocks = nn.ModuleList([_Block(dim, ffn_dim, added_kv_proj_dim, dt, device) for _ in range(num_layers)])
+        self.proj_out = _P((out_channels * math.prod(patch_size), dim), (out_channels * math.prod(patch_size),), dt, device)
+        self.scale_shift_table = nn.Parameter(torch.empty(1, 2, dim, dtype=torch.float32, device=device), requires_grad=False)
+        self._handle = None
+        self._packed = False
+        self._pack_keepalive: Dict[str, torch.Tensor] = {}
+        self._workspaces: Dict[Tuple, torch.Tensor] = {}
+        self.last_block0: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    @property
+    def dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+    @property
+    def device(self) -> torch.device:
+        return self.patch_embedding.weight.device
+
+    def _apply(self, fn, *a, **k):
+        # .to()/.cuda()/.cpu() re-allocate parameters: the fused device buffers must be rebuilt
+        self._packed = False
+        return super()._apply(fn, *a, **k)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().ce_dit_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _cfg_c(self) -> DiTConfigC:
+        c = self.config
+        return DiTConfigC(
+            c.num_attention_heads, c.attention_head_dim, c.in_channels, c.out_channels, c.text_dim, c.freq_dim, c.ffn_dim,
+            c.num_layers, c.image_dim or 0, c.added_kv_proj_dim or 0, c.rope_max_seq_len, c.rope_temporal_skip_len, c.eps,
+            *c.patch_size)
+
+    @torch.no_grad()
+    def pack_weights(self) -> None:
+        """Build the fused buffers the kernels read (QKV / KV rows stacked, scale_shift_tables stacked) and register
+        every parameter with the C handle.  The reference parameters become VIEWS of the fused buffers, so no memory
+        is duplicated and later in-place updates (e.g. a fused LoRA) are seen by the kernels.  Called lazily by
+        forward(); call it again after replacing parameter tensors."""
+        L = _lib.lib()
+        dev = self.device
+        if dev.type != "cuda":
+            raise CEError("ChronoEditTransformer3DModel must live on a CUDA (sm_100) device; there is no CPU path")
+        for n, p in self.named_parameters():
+            want = torch.float32 if any(k in n for k in KEEP_FP32) else torch.bfloat16
+            if p.dtype != want:
+                p.data = p.data.to(want)
+        if self._handle is None:
+            h = _lib.c_void_p()
+            cfg = self._cfg_c()
+            check(L.ce_dit_create(_lib.ctypes.byref(cfg), _lib.ctypes.byref(h)))
+            self._handle = h
+        keep: Dict[str, torch.Tensor] = {}
+
+        def fuse(prefix, holders, attr):
+            parts = [getattr(m, attr) for m in holders]
+            fused = torch.cat([p.data for p in parts], dim=0).contiguous()
+            off = 0
+            for p in parts:
+                n0 = p.shape[0]
+                p.data = fused[off: off + n0]
+                off += n0
+            keep[prefix + "." + attr] = fused
+            return fused
+
+        def reg(name, t):
+            t = t.contiguous() if not t.is_contiguous() else t
+            keep[name] = t
+            check(L.ce_dit_set_weight(self._handle, name.encode(), ptr(t), 1 if t.dtype == torch.float32 else 0, t.numel()))
+
+        fused_names = set()
+        for i, blk in enumerate(self.blocks):
+            p = f"blocks.{i}."
+            for attr in ("weight", "bias"):
+                reg(p + "attn1.to_qkv." + attr, fuse(p + "attn1.to_qkv", [blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v], attr))
+                reg(p + "attn2.to_kv." + attr, fuse(p + "attn2.to_kv", [blk.attn2.to_k, blk.attn2.to_v], attr))
+                if self.config.image_dim is not None:
+                    reg(p + "attn2.add_kv_proj." + attr, fuse(p + "attn2.add_kv_proj", [blk.attn2.add_k_proj, blk.attn2.add_v_proj], attr))
+            fused_names.update(p + s for s in ("attn1.to_q.", "attn1.to_k.", "attn1.to_v.", "attn2.to_k.", "attn2.to_v.",
+                                               "attn2.add_k_proj.", "attn2.add_v_proj."))
+        table = torch.cat([blk.scale_shift_table.data for blk in self.blocks], dim=0).contiguous()  # [layers, 6, D]
+        for i, blk in enumerate(self.blocks):
+            blk.scale_shift_table.data = table[i: i + 1]
+        reg("blocks.scale_shift_table", table)
+        for n, p in self.named_parameters():
+            if any(n.startswith(f) for f in fused_names) or (n.startswith("blocks.") and n.endswith("scale_shift_table")):
+                continue
+            reg(n, p.data)
+        check(L.ce_dit_weights_complete(self._handle))
+        self._pack_keepalive = keep
+        self._packed = True
+
+    def _workspace(self, B, T, H, W, Lt) -> torch.Tensor:
+        key = (B, T, H, W, Lt, str(self.device))
+        ws = self._workspaces.get(key)
+        if ws is None:
+            n = _lib.lib().ce_dit_workspace_bytes(self._handle, B, T, H, W, Lt)
+            if n < 0:
+                check(-1)
+            self._workspaces.clear()  # one live geometry at a time keeps the footprint bounded
+            ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._workspaces[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        timestep: torch.LongTensor,
+        encoder_hidden_states: torch.Tensor,
+        encoder_hidden_states_image: Optional[torch.Tensor] = None,
+        return_dict: bool = True,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+        return_block0: bool = False,
+    ) -> Union[Transformer2DModelOutput, Tuple[torch.Tensor]]:
+        # attention_kwargs["scale"] only matters for un-fused PEFT LoRA layers (transformer_chronoedit.py:406-419);
+        # the CLI fuses LoRA into the weights before inference, so it is accepted and ignored like the non-PEFT branch.
+        if not self._packed:
+            self.pack_weights()
+        dev = self.device
+        if hidden_states.dim() != 5:
+            raise CEError("hidden_states must be [B, C, T, H, W]")
+        B, C, T, H, W = hidden_states.shape
+        if C != self.config.in_channels:
+            raise CEError(f"hidden_states has {C} channels, model expects {self.config.in_channels}")
+        if (encoder_hidden_states_image is None) != (self.config.image_dim is None):
+            raise CEError("encoder_hidden_states_image must be passed iff the model was built with image_dim")
+        x = hidden_states.to(device=dev, dtype=torch.bfloat16).contiguous()
+        t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        if t.numel() == 1 and B > 1:
+            t = t.expand(B)
+        t = t.contiguous()
+        txt = encoder_hidden_states.to(device=dev, dtype=torch.bfloat16).contiguous()
+        img = None
+        if encoder_hidden_states_image is not None:
+            img = encoder_hidden_states_image.to(device=dev, dtype=torch.bfloat16).contiguous()
+            if img.shape[1] != 257:
+                raise CEError("encoder_hidden_states_image must have 257 tokens (transformer_chronoedit.py:53)")
+        Lt = txt.shape[1]
+        ws = self._workspace(B, T, H, W, Lt)
+        out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16, device=dev)
+        b0 = None
+        if return_block0:
+            L_tok = T * (H // 2) * (W // 2)
+            b0 = torch.empty(B * L_tok, self.config.num_attention_heads * self.config.attention_head_dim, dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().ce_dit_forward(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws),
+                                           ws.numel(), ptr(b0), current_stream()))
+        self.last_block0 = b0
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    @torch.no_grad()
+    def forward_host(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                     encoder_hidden_states_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end variant: all tensors are (pinned) HOST bf16/fp32 tensors; H2D, forward and D2H happen inside the
+        C-ABI call (ce_dit_forward_host).  Returns the host sample tensor."""
+        if not self._packed:
+            self.pack_weights()
+        B, C, T, H, W = hidden_states.shape
+        Lt = encoder_hidden_states.shape[1]
+        for tns in (hidden_states, encoder_hidden_states):
+            if tns.device.type != "cpu" or tns.dtype != torch.bfloat16 or not tns.is_contiguous():
+                raise CEError("forward_host expects contiguous CPU bf16 tensors")
+        t = timestep.to(torch.float32).contiguous()
+        L = _lib.lib()
+        ws = self._workspace(B, T, H, W, Lt)
+        n = L.ce_dit_host_staging_bytes(self._handle, B, T, H, W, Lt)
+        st = self._workspaces.get("staging")
+        if st is None or st.numel() < n:
+            st = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._workspaces["staging"] = st
+        if out is None:
+            out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16).pin_memory()
+        with torch.cuda.device(self.device):
+            check(L.ce_dit_forward_host(self._handle, ptr(hidden_states), ptr(t), ptr(encoder_hidden_states),
+                                        ptr(encoder_hidden_states_image), ptr(out), B, T, H, W, Lt, ptr(st), st.numel(), ptr(ws),
+                                        ws.numel(), current_stream()))
+        return out
+
+    def launches_per_forward(self) -> int:
+        return int(_lib.lib().ce_dit_last_launch_count(self._handle)) if self._handle else 0
+
+    # ------------------------------------------------------------------------------------------ loading
+    @classmethod
+    def from_config(cls, config: Dict[str, Any], **kw) -> "ChronoEditTransformer3DModel":
+        fields = ("patch_size", "num_attention_heads", "attention_head_dim", "in_channels", "out_channels", "text_dim", "freq_dim",
+                  "ffn_dim", "num_layers", "cross_attn_norm", "qk_norm", "eps", "image_dim", "added_kv_proj_dim",
+                  "rope_max_seq_len", "rope_temporal_skip_len")
+        return cls(**{k: config[k] for k in fields if k in config}, **kw)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None,
+                        torch_dtype: torch.dtype = torch.bfloat16, device: Optional[Union[str, torch.device]] = None,
+                        **unused) -> "ChronoEditTransformer3DModel":
+        """Load a diffusers-format checkpoint directory (config.json + diffusion_pytorch_model*.safetensors), the layout
+        `run_inference_diffusers.py:349-353` reads.  Local paths only (no hub download)."""
+        from safetensors import safe_open
+
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(root, cls.config_name)) as f:
+            cfg = json.load(f)
+        model = cls.from_config(cfg, torch_dtype=torch_dtype, device=device or "cpu")
+        index = os.path.join(root, "diffusion_pytorch_model.safetensors.index.json")
+        if os.path.exists(index):
+            with open(index) as f:
+                files = sorted(set(json.load(f)["weight_map"].values()))
+        else:
+            files = ["diffusion_pytorch_model.safetensors"]
+        params = dict(model.named_parameters())
+        seen = set()
+        for fn in files:
+            with safe_open(os.path.join(root, fn), framework="pt", device="cpu") as sf:
+                for k in sf.keys():
+                    if "norm_added_q" in k:  # `_keys_to_ignore_on_load_unexpected` (transformer_chronoedit.py:339)
+                        continue
+                    if k not in params:
+                        raise CEError(f"unexpected key in checkpoint: {k}")
+                    params[k].data.copy_(sf.get_tensor(k).reshape(params[k].shape))
+                    seen.add(k)
+        missing = sorted(set(params) - seen)
+        if missing:
+            raise CEError(f"checkpoint is missing {len(missing)} parameters, first: {missing[0]}")
+        return model

@@ -1,0 +1,133 @@
+/*
+ * chronoedit_b200 — C ABI of the B200-native ChronoEdit denoising hot path.
+ *
+ * The reference (nv-tlabs/ChronoEdit) has no FFI for this path: the boundary is two Python objects registered
+ * into a diffusers pipeline (pipeline_chronoedit.py:175-183).  This header is the C-ABI underneath the Python
+ * mirror classes in chronoedit_b200/ (INTEGRATION.md shows the ctypes binding); each entry point names the
+ * reference interface it stands in for.
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - activations / weights are bf16 unless stated; tensors are dense row-major in the layouts given;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never synchronise the device
+ *     (the *_host variants synchronise `stream` before returning because they hand results back in host memory);
+ *   - return value 0 = success, negative = failure (ce_last_error() holds the message of the calling thread's last
+ *     failure); there is NO CPU fallback: on a machine without an sm_100 GPU every compute entry point fails;
+ *   - one handle may be used from one thread at a time; distinct handles are independent.
+ */
+#ifndef CHRONOEDIT_B200_H_
+#define CHRONOEDIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CE_ABI_VERSION 1
+
+int ce_abi_version(void);
+const char* ce_last_error(void);
+/* 0 iff the current CUDA device is sm_100 (B200). */
+int ce_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * DiT: ChronoEditTransformer3DModel  (chronoedit_diffusers/transformer_chronoedit.py:298-476)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ce_dit ce_dit;
+
+typedef struct ce_dit_config {   /* = the @register_to_config arguments, transformer_chronoedit.py:342-360 */
+  int32_t num_attention_heads;   /* 40 */
+  int32_t attention_head_dim;    /* 128 (only value built) */
+  int32_t in_channels;           /* 36 */
+  int32_t out_channels;          /* 16 */
+  int32_t text_dim;              /* 4096 */
+  int32_t freq_dim;              /* 256 */
+  int32_t ffn_dim;               /* 13824 */
+  int32_t num_layers;            /* 40 */
+  int32_t image_dim;             /* 1280; 0 = no image embedder / no added k,v projections */
+  int32_t added_kv_proj_dim;     /* 5120 */
+  int32_t rope_max_seq_len;      /* 1024 */
+  int32_t rope_temporal_skip_len;/* 8 */
+  float eps;                     /* 1e-6 */
+  int32_t patch_t, patch_h, patch_w; /* (1,2,2) (only value built) */
+} ce_dit_config;
+
+/* ChronoEditTransformer3DModel.__init__ (:342-395).  No weights are allocated: the caller owns them. */
+int ce_dit_create(const ce_dit_config* cfg, ce_dit** out);
+void ce_dit_destroy(ce_dit* h);
+
+/* Register one parameter by name (device pointer, kept alive by the caller until ce_dit_destroy).
+ * Names are the reference state_dict's (e.g. "blocks.3.ffn.net.2.weight") except for the fused / stacked buffers the
+ * Python mirror builds as views over the reference parameters:
+ *   blocks.N.attn1.to_qkv.{weight,bias}      [3D,D] / [3D]   rows = to_q | to_k | to_v
+ *   blocks.N.attn2.to_kv.{weight,bias}       [2D,D] / [2D]   rows = to_k | to_v
+ *   blocks.N.attn2.add_kv_proj.{weight,bias} [2D,Da]/ [2D]   rows = add_k_proj | add_v_proj
+ *   blocks.scale_shift_table                 [num_layers,6,D] fp32 (stack of blocks.N.scale_shift_table)
+ *   patch_embedding.weight                   [D, Cin*pt*ph*pw] (the Conv3d weight, flattened)
+ * dtype: 0 = bf16, 1 = fp32.  fp32 is required for (and only for) the reference's `_keep_in_fp32_modules`
+ * (time_embedder, scale_shift_table, norm1/norm2/norm3 affine parameters, :338). */
+int ce_dit_set_weight(ce_dit* h, const char* name, const void* ptr, int dtype, int64_t numel);
+/* 0 when every parameter the configuration needs has been registered; otherwise fails and names the first missing. */
+int ce_dit_weights_complete(const ce_dit* h);
+
+/* Scratch bytes one forward needs for `batch` samples of latent geometry (frames, height, width) and text_len tokens. */
+int64_t ce_dit_workspace_bytes(const ce_dit* h, int batch, int frames, int height, int width, int text_len);
+
+/* ChronoEditTransformer3DModel.forward (:397-476).
+ *   hidden_states [B, in_channels, frames, height, width]   timestep [B] fp32 (the pipeline's int64 t cast to float, :155-157)
+ *   encoder_hidden_states [B, text_len, text_dim]           encoder_hidden_states_image [B, 257, image_dim] or NULL
+ *   sample (out) [B, out_channels, frames, height, width]
+ * frames must be 2 or rope_temporal_skip_len (the reference asserts this, :205).
+ * intermediates: optional; when non-NULL receives block 0's output [B*L, D] bf16 (parity tests). */
+int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, const void* encoder_hidden_states,
+                   const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
+                   int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* stream);
+
+/* Same call with every tensor in (pinned) HOST memory: H2D copies of the inputs, forward, D2H of the sample, all on
+ * `stream`, which is synchronised before returning.  `staging` is a device buffer of at least
+ * ce_dit_host_staging_bytes(...) bytes.  This is the end-to-end ("e2e") path bench.py times. */
+int64_t ce_dit_host_staging_bytes(const ce_dit* h, int batch, int frames, int height, int width, int text_len);
+int ce_dit_forward_host(ce_dit* h, const void* hidden_states_host, const float* timestep_host,
+                        const void* encoder_hidden_states_host, const void* encoder_hidden_states_image_host,
+                        void* sample_host, int batch, int frames, int height, int width, int text_len, void* staging,
+                        int64_t staging_bytes, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Kernel launches issued by the last ce_dit_forward on this handle (bench.py's "gpu_launches"). */
+int64_t ce_dit_last_launch_count(const ce_dit* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Individual hot-path operators (used by the handle above; exported for operator-level parity tests / profiling)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* out[M,N] = epilogue(A[M,K] x W[N,K]^T + bias): one nn.Linear (+ fused elementwise tail).
+ * epilogue: 0 bias | 1 bias+GELU(tanh) | 2 bias+GELU(erf) | 3 bias, gate*y + resid (fp32) | 4 bias, y + resid
+ * out_f32 (optional, [M,N]): acc + bias in fp32 before any rounding. */
+int ce_linear_bf16(const void* A, int lda, const void* W, int ldw, const void* bias, void* out, int ldo, float* out_f32,
+                   int M, int N, int K, int epilogue, const void* resid, int ldr, const float* gate, int gate_stride,
+                   int rows_per_batch, void* stream);
+
+/* F.scaled_dot_product_attention (non-causal, no mask, head_dim 128) on [B, L, H*128]-strided q/k/v
+ * (transformer_chronoedit.py:91-99).  accumulate=1 adds into `out` in bf16 (text + image cross-attention, :103-104). */
+int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
+                      int H, int Lq, int Lk, float scale, int accumulate, void* stream);
+
+/* FP32LayerNorm (+ adaLN modulate or affine) over the last dim of x[rows, D] -> y (bf16). (:279, :284, :289, :460) */
+int ce_layernorm_bf16(const void* x, int ldx, void* y, int ldy, int rows, int D, float eps, const float* scale,
+                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
+                      void* stream);
+
+/* diffusers RMSNorm across heads, then optional interleaved RoPE, in place (:62-65, :71-79).
+ * rope_cos / rope_sin: fp32 [L, head_dim/2] or NULL. */
+int ce_rmsnorm_rope_bf16(void* x, int ldx, int rows, int D, float eps, const void* weight, const float* rope_cos,
+                         const float* rope_sin, int L, int head_dim, void* stream);
+
+/* ChronoEditRotaryPosEmbed.forward (:168-213) as fp32 cos/sin tables [L, head_dim/2] written to HOST arrays. */
+int ce_rope_table_host(int head_dim, int frames, int height_patches, int width_patches, int max_seq_len,
+                       int temporal_skip_len, float theta, float* cos_out_host, float* sin_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHRONOEDIT_B200_H_ */
