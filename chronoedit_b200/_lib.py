@@ -43,6 +43,8 @@ SIGNATURES = {
     "ce_dit_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "ce_dit_last_launch_count": (c_int64, [c_void_p]),
+    "ce_dit_profile_begin": (c_int, [c_void_p, c_int]),
+    "ce_dit_profile_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ce_linear_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ce_attention_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,

@@ -38,7 +38,15 @@ struct ce_dit {
   float* rope_cos = nullptr;
   float* rope_sin = nullptr;
   int64_t launches = 0;
+  // optional per-category device timing (CUDA events on the launch stream around every kernel)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;       // pairs (begin, end)
+  std::vector<int> ev_cat;
+  std::vector<double> ev_work;       // algorithmic flops (cat 0,1) or bytes (cat 2) of the launch
+  size_t ev_used = 0;
 };
+
+enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWS = 2, CAT_OTHER = 3, NUM_CATS = 4 };
 
 namespace {
 
@@ -245,7 +253,27 @@ int ensure_rope(ce_dit* h, int frames, int hp, int wp, cudaStream_t stream) {
 
 #define W_BF16(name) reinterpret_cast<const bf16*>(h->w.at(name).ptr)
 #define W_F32(name) reinterpret_cast<const float*>(h->w.at(name).ptr)
-#define RUN(call)            \
+static inline void prof_begin(ce_dit* h, int cat, double work, cudaStream_t s) {
+  if (!h->profiling || h->ev_used + 2 > h->ev.size()) return;
+  cudaEventRecord(h->ev[h->ev_used], s);
+  h->ev_cat[h->ev_used / 2] = cat;
+  h->ev_work[h->ev_used / 2] = work;
+}
+static inline void prof_end(ce_dit* h, cudaStream_t s) {
+  if (!h->profiling || h->ev_used + 2 > h->ev.size()) return;
+  cudaEventRecord(h->ev[h->ev_used + 1], s);
+  h->ev_used += 2;
+}
+#define RUNC(cat, work, call)          \
+  do {                                 \
+    prof_begin(h, (cat), (work), s);   \
+    int _rc = (call);                  \
+    if (_rc) return _rc;               \
+    prof_end(h, s);                    \
+    ++h->launches;                     \
+  } while (0)
+#define RUN(call) RUNC(CAT_OTHER, 0.0, call)
+#define RUN2(call)           \
   do {                       \
     int _rc = (call);        \
     if (_rc) return _rc;     \
@@ -261,7 +289,16 @@ static int linear(ce_dit* h, const bf16* A, int lda, const std::string& wname, i
   g.epi = epi;
   g.resid = resid; g.ldr = ldr;
   g.gate = gate; g.gate_stride = gate_stride; g.rows_per_batch = rows_per_batch;
-  return launch_gemm_bf16(A, lda, W_BF16(wname + ".weight"), K, g, s);
+  prof_begin(h, CAT_GEMM, 2.0 * M * (double)N * K, s);
+  int rc = launch_gemm_bf16(A, lda, W_BF16(wname + ".weight"), K, g, s);
+  if (rc == 0) prof_end(h, s);
+  return rc;
+}
+static int attention(ce_dit* h, const AttnArgs& a, cudaStream_t s) {
+  prof_begin(h, CAT_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * a.head_dim, s);
+  int rc = launch_attention(a, s);
+  if (rc == 0) prof_end(h, s);
+  return rc;
 }
 
 extern "C" {
@@ -289,6 +326,7 @@ void ce_dit_destroy(ce_dit* h) {
   if (!h) return;
   if (h->rope_cos) cudaFree(h->rope_cos);
   if (h->rope_sin) cudaFree(h->rope_sin);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -326,6 +364,42 @@ int64_t ce_dit_workspace_bytes(const ce_dit* h, int batch, int frames, int heigh
 
 int64_t ce_dit_last_launch_count(const ce_dit* h) { return h ? h->launches : 0; }
 
+int ce_dit_profile_begin(ce_dit* h, int max_launches) {
+  CE_REQUIRE(h && max_launches > 0, "ce_dit_profile_begin: arguments");
+  while ((int)h->ev.size() < 2 * max_launches) {
+    cudaEvent_t e;
+    CE_CHECK_CUDA(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  h->ev_cat.assign(h->ev.size() / 2, 0);
+  h->ev_work.assign(h->ev.size() / 2, 0.0);
+  h->ev_used = 0;
+  h->profiling = true;
+  return CE_OK;
+}
+
+int ce_dit_profile_end(ce_dit* h, double* ms_out, double* work_out, int64_t* count_out) {
+  CE_REQUIRE(h && ms_out && work_out && count_out, "ce_dit_profile_end: arguments");
+  h->profiling = false;
+  for (int c = 0; c < NUM_CATS; ++c) {
+    ms_out[c] = 0.0;
+    work_out[c] = 0.0;
+    count_out[c] = 0;
+  }
+  if (h->ev_used == 0) return CE_OK;
+  CE_CHECK_CUDA(cudaEventSynchronize(h->ev[h->ev_used - 1]));
+  for (size_t i = 0; i + 1 < h->ev_used + 1 && i < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CE_CHECK_CUDA(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    const int c = h->ev_cat[i / 2];
+    ms_out[c] += ms;
+    work_out[c] += h->ev_work[i / 2];
+    count_out[c] += 1;
+  }
+  h->ev_used = 0;
+  return CE_OK;
+}
+
 int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, const void* encoder_hidden_states,
                    const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
                    int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* stream_v) {
@@ -352,7 +426,7 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
 
   // ---- patch embedding (Conv3d k=s=(1,2,2) as im2row + GEMM, :429-430)
   RUN(launch_patchify(reinterpret_cast<const bf16*>(hidden_states), ws.patches, B, c.in_channels, frames, height, width, s));
-  RUN(linear(h, ws.patches, Kp, "patch_embedding", M, D, Kp, ws.x, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+  RUN2(linear(h, ws.patches, Kp, "patch_embedding", M, D, Kp, ws.x, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
 
   // ---- condition embedder (:147-165)
   RUN(launch_timestep_sinusoid(timestep, ws.sin_emb, B, c.freq_dim, s));
@@ -365,15 +439,15 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
   RUN(launch_add_table(W_F32("blocks.scale_shift_table"), c.num_layers, ws.tproj, 6 * D, ws.mod, B, D, 6, s));
   RUN(launch_add_table(W_F32("scale_shift_table"), 1, ws.temb_bf16, D, ws.modf, B, D, 2, s));
   // text: Linear -> GELU(tanh) -> Linear
-  RUN(linear(h, reinterpret_cast<const bf16*>(encoder_hidden_states), c.text_dim, ce_ + "text_embedder.linear_1", B * Lt, D, c.text_dim,
+  RUN2(linear(h, reinterpret_cast<const bf16*>(encoder_hidden_states), c.text_dim, ce_ + "text_embedder.linear_1", B * Lt, D, c.text_dim,
              ws.text1, D, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
-  RUN(linear(h, ws.text1, D, ce_ + "text_embedder.linear_2", B * Lt, D, D, ws.ctx_text, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+  RUN2(linear(h, ws.text1, D, ce_ + "text_embedder.linear_2", B * Lt, D, D, ws.ctx_text, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
   if (c.image_dim > 0) {  // image: FP32LayerNorm -> Linear -> GELU(erf) -> Linear -> FP32LayerNorm (:111-123)
     const int I = c.image_dim;
     RUN(launch_layernorm(reinterpret_cast<const bf16*>(encoder_hidden_states_image), I, ws.img0, I, B * Li, I, 1e-5f, nullptr, nullptr, 0, 0,
                          W_F32(ce_ + "image_embedder.norm1.weight"), W_F32(ce_ + "image_embedder.norm1.bias"), s));
-    RUN(linear(h, ws.img0, I, ce_ + "image_embedder.ff.net.0.proj", B * Li, I, I, ws.img1, I, EPI_BIAS_GELU_ERF, nullptr, 0, nullptr, 0, 1, s));
-    RUN(linear(h, ws.img1, I, ce_ + "image_embedder.ff.net.2", B * Li, D, I, ws.img2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.img0, I, ce_ + "image_embedder.ff.net.0.proj", B * Li, I, I, ws.img1, I, EPI_BIAS_GELU_ERF, nullptr, 0, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.img1, I, ce_ + "image_embedder.ff.net.2", B * Li, D, I, ws.img2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
     RUN(launch_layernorm(ws.img2, D, ws.ctx_img, D, B * Li, D, 1e-5f, nullptr, nullptr, 0, 0, W_F32(ce_ + "image_embedder.norm2.weight"),
                          W_F32(ce_ + "image_embedder.norm2.bias"), s));
   }
@@ -383,10 +457,10 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     const std::string p = "blocks." + std::to_string(i) + ".";
     const float* mod = ws.mod + (size_t)i * B * 6 * D;  // [B, 6, D]: shift, scale, gate, c_shift, c_scale, c_gate
     // 1. self-attention
-    RUN(launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, s));
-    RUN(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-    RUN(launch_rmsnorm_rope(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
-    RUN(launch_rmsnorm_rope(ws.qkv + D, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_k.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, s));
+    RUN2(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv + D, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_k.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
     {
       AttnArgs a;
       a.B = B; a.H = H; a.Lq = L; a.Lk = L;
@@ -395,15 +469,15 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
       a.v = ws.qkv + 2 * D; a.ldv = 3 * D;
       a.out = ws.attn; a.ldo = D;
       a.scale = attn_scale;
-      RUN(launch_attention(a, s));
+      RUN2(attention(h, a, s));
     }
-    RUN(linear(h, ws.attn, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s));
+    RUN2(linear(h, ws.attn, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s));
     // 2. cross-attention
-    RUN(launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, nullptr, nullptr, 0, 0, W_F32(p + "norm2.weight"), W_F32(p + "norm2.bias"), s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, nullptr, nullptr, 0, 0, W_F32(p + "norm2.weight"), W_F32(p + "norm2.bias"), s));
     bf16* q2 = ws.qkv;  // [M, D]
-    RUN(linear(h, ws.xn, D, p + "attn2.to_q", M, D, D, q2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-    RUN(launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
-    RUN(linear(h, ws.ctx_text, D, p + "attn2.to_kv", B * Lt, 2 * D, D, ws.kv_text, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.xn, D, p + "attn2.to_q", M, D, D, q2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+    RUN2(linear(h, ws.ctx_text, D, p + "attn2.to_kv", B * Lt, 2 * D, D, ws.kv_text, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
     RUN(launch_rmsnorm_rope(ws.kv_text, 2 * D, B * Lt, D, c.eps, W_BF16(p + "attn2.norm_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
     {
       AttnArgs a;
@@ -413,10 +487,10 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
       a.v = ws.kv_text + D; a.ldv = 2 * D;
       a.out = ws.attn; a.ldo = D;
       a.scale = attn_scale;
-      RUN(launch_attention(a, s));
+      RUN2(attention(h, a, s));
     }
     if (c.image_dim > 0) {
-      RUN(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, ws.kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+      RUN2(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, ws.kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
       RUN(launch_rmsnorm_rope(ws.kv_img, 2 * D, B * Li, D, c.eps, W_BF16(p + "attn2.norm_added_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
       AttnArgs a;
       a.B = B; a.H = H; a.Lq = L; a.Lk = Li;
@@ -426,20 +500,20 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
       a.out = ws.attn; a.ldo = D;
       a.scale = attn_scale;
       a.accumulate = 1;
-      RUN(launch_attention(a, s));
+      RUN2(attention(h, a, s));
     }
-    RUN(linear(h, ws.attn, D, p + "attn2.to_out.0", M, D, D, ws.x, D, EPI_BIAS_RESID, ws.x, D, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.attn, D, p + "attn2.to_out.0", M, D, D, ws.x, D, EPI_BIAS_RESID, ws.x, D, nullptr, 0, 1, s));
     // 3. feed-forward
-    RUN(launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, s));
-    RUN(linear(h, ws.xn, D, p + "ffn.net.0.proj", M, F, D, ws.hbuf, F, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
-    RUN(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, s));
+    RUN2(linear(h, ws.xn, D, p + "ffn.net.0.proj", M, F, D, ws.hbuf, F, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s));
     if (i == 0 && block0_out)
       CE_CHECK_CUDA(cudaMemcpyAsync(block0_out, ws.x, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
   }
 
   // ---- output head (:451-467): modf = [B, 2, D] with shift = chunk 0, scale = chunk 1
-  RUN(launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, s));
-  RUN(linear(h, ws.xn, D, "proj_out", M, No, D, ws.yout, No, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+  RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, s));
+  RUN2(linear(h, ws.xn, D, "proj_out", M, No, D, ws.yout, No, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
   RUN(launch_unpatchify(ws.yout, No, reinterpret_cast<bf16*>(sample), B, c.out_channels, frames, height, width, s));
   return CE_OK;
 }

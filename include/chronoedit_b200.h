@@ -97,6 +97,14 @@ int ce_dit_forward_host(ce_dit* h, const void* hidden_states_host, const float* 
 /* Kernel launches issued by the last ce_dit_forward on this handle (bench.py's "gpu_launches"). */
 int64_t ce_dit_last_launch_count(const ce_dit* h);
 
+/* Device-side timing of the kernels of subsequent forwards: a CUDA event pair on the launch stream around every
+ * launch (up to max_launches; later launches are not recorded).  ce_dit_profile_end waits for the last recorded event
+ * and returns, per category c in {0: tcgen05 GEMM, 1: tcgen05 attention, 2: LayerNorm / RMSNorm row kernels,
+ * 3: everything else}: total milliseconds, total algorithmic work (FLOPs for 0/1, bytes for 2) and launch count
+ * (each array has 4 entries).  This is what bench.py's "roofline" object is computed from. */
+int ce_dit_profile_begin(ce_dit* h, int max_launches);
+int ce_dit_profile_end(ce_dit* h, double* ms_out, double* work_out, int64_t* count_out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Individual hot-path operators (used by the handle above; exported for operator-level parity tests / profiling)
  * ------------------------------------------------------------------------------------------------------------ */
