@@ -176,10 +176,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               y[0] += b0.x; y[1] += b0.y; y[2] += b1.x; y[3] += b1.y;
               y[4] += b2.x; y[5] += b2.y; y[6] += b3.x; y[7] += b3.y;
             }
+            if (g.bias_row) {
+              const float br = __bfloat162float(g.bias_row[row]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] += br;
+            }
             if (g.out_f32) {
               float4* o = reinterpret_cast<float4*>(g.out_f32 + (size_t)row * g.N + n);
               o[0] = make_float4(y[0], y[1], y[2], y[3]);
               o[1] = make_float4(y[4], y[5], y[6], y[7]);
+              if (!g.out) continue;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);  // nn.Linear returns bf16
@@ -251,7 +257,7 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
   CE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem");
   CE_REQUIRE(g.N % 8 == 0, "gemm: N must be a multiple of 8");
   CE_REQUIRE(g.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA strides)");
-  CE_REQUIRE(g.out != nullptr && g.ldo % 8 == 0, "gemm: out / ldo");
+  CE_REQUIRE((g.out != nullptr && g.ldo % 8 == 0) || (g.out == nullptr && g.out_f32 != nullptr), "gemm: out / ldo");
   CE_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
   if (g.epi == EPI_BIAS_GATE_RESID || g.epi == EPI_BIAS_RESID)
     CE_REQUIRE(g.resid != nullptr && g.ldr % 8 == 0, "gemm: residual epilogue needs resid / ldr");

@@ -31,7 +31,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(CE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -41,7 +41,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CE_ERR_INVALID, "TMA base pointer not 16-byte aligned");

@@ -40,8 +40,9 @@ int fail(int code, const std::string& msg);
 // ---- tensor maps ---------------------------------------------------------------------------
 // bf16 tensor, `rank` dims listed innermost first.  strides_bytes[i] is the byte stride of dim i+1
 // (dim 0 is contiguous).  128-byte swizzle, zero OOB fill.
+// elem_strides (optional): traversal stride per dim; TMA then fetches ceil(box[i] / elem_strides[i]) elements along dim i.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 // 2-D row-major [rows, cols] bf16 with leading dimension `ld` (elements); box = [box_rows, 64 cols].
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
