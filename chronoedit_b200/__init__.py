@@ -10,3 +10,6 @@ from ._lib import CEError, LIB_PATH, lib  # noqa: F401
 from .transformer import ChronoEditTransformer3DModel, Transformer2DModelOutput  # noqa: F401
 
 __all__ = ["ChronoEditTransformer3DModel", "Transformer2DModelOutput", "CEError", "lib", "LIB_PATH"]
+from .autoencoder import AutoencoderKLWan  # noqa: E402,F401
+
+__all__.append("AutoencoderKLWan")

@@ -17,6 +17,11 @@ class CEError(RuntimeError):
     pass
 
 
+class VAEConfigC(ctypes.Structure):
+    _fields_ = [("dim", c_int32), ("z_dim", c_int32), ("dim_mult", c_int32 * 4), ("num_res_blocks", c_int32),
+                ("temporal_downsample", c_int32 * 3)]
+
+
 class DiTConfigC(ctypes.Structure):
     _fields_ = [
         ("num_attention_heads", c_int32), ("attention_head_dim", c_int32), ("in_channels", c_int32),
@@ -45,6 +50,15 @@ SIGNATURES = {
     "ce_dit_last_launch_count": (c_int64, [c_void_p]),
     "ce_dit_profile_begin": (c_int, [c_void_p, c_int]),
     "ce_dit_profile_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ce_vae_create": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ce_vae_destroy": (None, [c_void_p]),
+    "ce_vae_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "ce_vae_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int]),
+    "ce_vae_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "ce_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "ce_vae_last_launch_count": (c_int64, [c_void_p]),
+    "ce_conv3d_cl_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ce_linear_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ce_attention_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,

@@ -172,7 +172,7 @@ conv3d_cl_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
               if (n + j < a.Cout) {
                 float o = y[j];
                 if (a.clamp) o = fminf(fmaxf(o, -1.0f), 1.0f);
-                a.y[(((size_t)(n + j) * a.Tout + to) * a.Hout + oh) * a.Wout + ow] = __float2bfloat16_rn(o);
+                a.y[(((size_t)(n + j) * a.planar_T + a.planar_t0 + to) * a.Hout + oh) * a.Wout + ow] = __float2bfloat16_rn(o);
               }
             }
             continue;

@@ -27,8 +27,9 @@ struct ConvArgs {
   // epilogue
   const bf16* resid = nullptr;   // optional, same geometry as y: y = bf16(float(bf16(conv)) + float(resid))   (ResidualBlock x + h)
   int split_time = 0;            // 1: Cout = 2*C; channel n goes to frame 2*to + n / C, channel n % C (upsample3d interleave, wan2pt1.py:137-139)
-  int planar_out = 0;            // 1: y is planar [Cout, Tout, Hout, Wout] (NCTHW) and values are clamped to [-1, 1] when clamp != 0
-  int clamp = 0;
+  int planar_out = 0;            // 1: y is planar [Cout, planar_T, Hout, Wout] (NCTHW), frame `to` stored at planar_t0 + to; values
+  int clamp = 0;                 //    are clamped to [-1, 1] when clamp != 0
+  int planar_T = 0, planar_t0 = 0;
 };
 
 int launch_conv3d_cl(const ConvArgs& a, cudaStream_t stream);

@@ -256,7 +256,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmArgs& g, cudaStream_t stream) {
   CE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem");
   CE_REQUIRE(g.N % 8 == 0, "gemm: N must be a multiple of 8");
-  CE_REQUIRE(g.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA strides)");
+  CE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda, ldw must be multiples of 8 (16-byte TMA strides)");
   CE_REQUIRE((g.out != nullptr && g.ldo % 8 == 0) || (g.out == nullptr && g.out_f32 != nullptr), "gemm: out / ldo");
   CE_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
   if (g.epi == EPI_BIAS_GATE_RESID || g.epi == EPI_BIAS_RESID)

@@ -106,10 +106,10 @@ __global__ void im2row_kernel(const bf16* __restrict__ x, size_t sc, size_t st, 
 
 // P[r, :] = softmax(S[r, :] * scale) in fp32, stored bf16.
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int cols, float scale) {
+softmax_rows_kernel(const float* __restrict__ S, int lds, bf16* __restrict__ P, int ldp, int cols, float scale) {
   __shared__ float red[32];
-  const float* s = S + (size_t)blockIdx.x * cols;
-  bf16* p = P + (size_t)blockIdx.x * cols;
+  const float* s = S + (size_t)blockIdx.x * lds;
+  bf16* p = P + (size_t)blockIdx.x * ldp;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) mx = fmaxf(mx, s[i]);
   mx = warp_max(mx);
@@ -177,8 +177,8 @@ int launch_im2row(const bf16* x, size_t sc, size_t st, size_t sh, size_t sw, int
   return CE_OK;
 }
 
-int launch_softmax_rows(const float* S, bf16* P, int rows, int cols, float scale, cudaStream_t stream) {
-  softmax_rows_kernel<<<rows, 256, 0, stream>>>(S, P, cols, scale);
+int launch_softmax_rows(const float* S, int lds, bf16* P, int ldp, int rows, int cols, float scale, cudaStream_t stream) {
+  softmax_rows_kernel<<<rows, 256, 0, stream>>>(S, lds, P, ldp, cols, scale);
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -106,8 +106,49 @@ int ce_dit_profile_begin(ce_dit* h, int max_launches);
 int ce_dit_profile_end(ce_dit* h, double* ms_out, double* work_out, int64_t* count_out);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Individual hot-path operators (used by the handle above; exported for operator-level parity tests / profiling)
+ * VAE: AutoencoderKLWan encode / decode as the pipeline uses them (pipeline_chronoedit.py:436-443, 776-781);
+ * arithmetic = WanVAE_ of chronoedit/_src/tokenizers/wan2pt1.py:467-581 WITHOUT the latent mean/std (the pipeline applies
+ * those itself, :427-445, :765-774).
  * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ce_vae ce_vae;
+
+typedef struct ce_vae_config {      /* _video_vae cfg, wan2pt1.py:597-605 */
+  int32_t dim;                      /* 96 */
+  int32_t z_dim;                    /* 16 */
+  int32_t dim_mult[4];              /* 1,2,4,4 */
+  int32_t num_res_blocks;           /* 2 */
+  int32_t temporal_downsample[3];   /* 0,1,1 */
+} ce_vae_config;
+
+int ce_vae_create(const ce_vae_config* cfg, ce_vae** out);
+void ce_vae_destroy(ce_vae* h);
+/* Parameters by the in-tree twin's names (e.g. "decoder.upsamples.3.time_conv.weight"), all bf16, PRE-PACKED by the caller:
+ *   convolution weights [Cout, Cin, kt, kh, kw] -> [Cout, taps, Cin_pad] with taps ordered (dt, dh, dw), Cin_pad = Cin rounded
+ *     up to 64 (zero filled) when Cin >= 64; for Cin < 64 -> [Cout, Kpad] with K = taps*Cin rounded up to 8;
+ *   "*.gamma" [C]; attention "to_qkv.weight" [3C, C], "proj.weight" [C, C]; biases [Cout]. */
+int ce_vae_set_weight(ce_vae* h, const char* name, const void* ptr, int64_t numel);
+/* decode != 0: (frames, height, width) is the LATENT geometry; else the PIXEL geometry. */
+int64_t ce_vae_workspace_bytes(ce_vae* h, int decode, int frames, int height, int width);
+/* video [3, frames, height, width] (planar, one sample, values in [-1,1], frames = 1+4k) -> posterior moments
+ * [2*z_dim, 1+k, height/8, width/8]: channels [0,z) = mean (= AutoencoderKLWan.encode(x).latent_dist.mode()), [z,2z) = logvar */
+int ce_vae_encode(ce_vae* h, const void* video, void* moments, int frames, int height, int width, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+/* z [z_dim, Tl, h, w] -> video [3, 1+4(Tl-1), 8h, 8w]; clamp != 0 clamps to [-1,1] (= AutoencoderKLWan.decode(z)[0]) */
+int ce_vae_decode(ce_vae* h, const void* z, void* video, int latent_frames, int latent_height, int latent_width, int clamp,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int64_t ce_vae_last_launch_count(const ce_vae* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Individual hot-path operators (used by the handles above; exported for operator-level parity tests / profiling)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* One channels-last convolution on the tcgen05 implicit-GEMM kernel (CausalConv3d / Conv2d of wan2pt1.py:42-60, 98-110):
+ *   y[to,oh,ow,n] = bias[n] + sum W[n,(dt,dh,dw),c] * x[t_base + to*st + dt, oh*sh + dh - ph, ow*sw + dw - pw, c]
+ * x [Tin,Hin,Win,Cin], w packed [Cout, taps, Cin_pad64], y [Tout,Hout,Wout,Cout] (split_time: [2*Tout,...,Cout/2]),
+ * resid optional (same geometry as y). */
+int ce_conv3d_cl_bf16(const void* x, int Tin, int Hin, int Win, int Cin, const void* w, const void* bias, int Cout, int kt,
+                      int kh, int kw, int st, int sh, int sw, int ph, int pw, int t_base, void* y, int Tout, int Hout, int Wout,
+                      const void* resid, int split_time, void* stream);
 
 /* out[M,N] = epilogue(A[M,K] x W[N,K]^T + bias): one nn.Linear (+ fused elementwise tail).
  * epilogue: 0 bias | 1 bias+GELU(tanh) | 2 bias+GELU(erf) | 3 bias, gate*y + resid (fp32) | 4 bias, y + resid
