@@ -2,12 +2,13 @@
 //
 //   out[b, i, h*128:(h+1)*128] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) @ v[b,j,h,:]
 //
-// One CTA per (128-query tile, head, batch); 320 threads:
+// One CTA per (128-query tile, head, batch); 384 threads = 3 warpgroups (registers re-partitioned with setmaxnreg):
 //   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (128 keys) through 2-deep rings
 //   warp 1      MMA issuer:   S_j = Q K_j^T  (M128 N128 K128, accumulator S_{j&1} in TMEM)
 //                             O_{j&1} += P_j V_j (P_j from shared memory, V_j as MN-major B operand)
-//   warps 2-5   softmax group 0 (even key tiles), warps 6-9 softmax group 1 (odd key tiles):
-//               TMEM -> registers, running max / sum (fp32), exp2, bf16 P -> shared memory (128B-swizzled A tile)
+//   warps 4-7   softmax group 0 (even key tiles), warps 8-11 softmax group 1 (odd key tiles): the thread's whole
+//               128-wide score row TMEM -> registers in one go, max / exp2 / sum as independent chains (fp32),
+//               bf16 P -> shared memory (128B-swizzled A tile)
 // The two groups keep INDEPENDENT online-softmax streams (own max, sum and O accumulator) that are merged once
 // at the end, so S_{j+1} and softmax_j / PV_j overlap without any cross-group exchange in the loop.
 // O is rescaled lazily: only when the row max grows by more than 2^8 (values stay bounded, result identical
@@ -27,7 +28,7 @@ namespace {
 constexpr int HD = 128;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int ATTN_THREADS = 320;
+constexpr int ATTN_THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 16 KB [128 x 64] swizzled blocks
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
@@ -75,6 +76,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register re-partition (warpgroup-aligned): the producer / MMA warpgroup gives its registers to the softmax warpgroups
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -139,9 +143,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         umma_commit(&bars[PV_DONE + g]);
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ---------------------------------------------------------------- softmax groups
-    const int g = (warp - 2) >> 2;       // 0: even key tiles, 1: odd key tiles
+    const int g = (warp - 4) >> 2;       // 0: even key tiles, 1: odd key tiles
     const int quad = warp & 3;           // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;      // query row inside the tile
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
@@ -157,19 +163,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       const int valid = a.Lk - j * BKV;  // >= 1; >= 128 means no masking
       mbar_wait(&bars[S_FULL + g], t & 1, 60 + g);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(s_tmem + c * 32, s);
-        tmem_ld_wait();
+      // the whole 128-wide score row of this thread goes to registers with one wait (4 x tcgen05.ld in flight)
+      uint32_t s[128];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = __uint_as_float(s[i]);
-          mx = (c * 32 + i < valid) ? fmaxf(mx, x) : mx;
-        }
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      tmem_ld_wait();
+      if (valid < BKV) {  // last key tile only (warp-uniform): masked scores -> -inf -> p = 0
+#pragma unroll
+        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
       }
+      // row max with 8 independent chains (a single fmax chain would cost 128 x 4 dependent cycles)
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
+      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       mx *= sl2;
       if (t == 0) {
         m = mx;
@@ -193,21 +202,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           tmem_st_wait();
         }
       }
-      // pass 2: p = exp2(s*scale*log2e - m) -> bf16 -> shared memory (K-major, 128B swizzle: chunk ^= row & 7)
-      float lsum = 0.f;
-#pragma unroll 1
+      // p = exp2(s*scale*log2e - m) -> bf16 -> shared memory (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
+      const float neg_m = -m;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(s_tmem + c * 32, s);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(__uint_as_float(s[2 * i]) * sl2 - m);
-          float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) * sl2 - m);
-          p0 = (c * 32 + 2 * i < valid) ? p0 : 0.f;
-          p1 = (c * 32 + 2 * i + 1 < valid) ? p1 : 0.f;
-          lsum += p0 + p1;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[32 * c + 2 * i]), sl2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[32 * c + 2 * i + 1]), sl2, neg_m));
+          sum4[i & 3] += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
         uint8_t* row_base = p_smem + (c >> 1) * HALF_BYTES + r * 128;
@@ -217,7 +222,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           *reinterpret_cast<uint4*>(row_base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
       }
-      l += lsum;
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bars[P_FULL + g]);

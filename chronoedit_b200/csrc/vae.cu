@@ -8,6 +8,7 @@
 // (3->dim, z->top, 2z->2z) go through im2row + the tcgen05 GEMM; RMS_norm+SiLU / upsample / softmax are the row kernels
 // of vae_kernels.cu; the single-head mid attention is GEMM (QK^T, fp32) -> row softmax -> GEMM (P V).
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -19,6 +20,18 @@
 #include "vae_kernels.cuh"
 
 using namespace ce;
+
+// CE_VAE_DEBUG=1: after every op, synchronise and print non-finite count / mean |x| of its output (debug only).
+__global__ void vae_debug_stats_kernel(const bf16* x, size_t n, unsigned long long* bad, float* sum) {
+  float s = 0.f;
+  unsigned long long b = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    if (!isfinite(v)) ++b; else s += fabsf(v);
+  }
+  atomicAdd(sum, s);
+  if (b) atomicAdd(bad, b);
+}
 
 struct VWeight {
   const void* ptr = nullptr;
@@ -94,6 +107,26 @@ struct Run {
     if (r && !rc) rc = r;
     if (!r) ++h->launches;
   }
+  void debug(const std::string& what, const bf16* p, size_t n) {
+    static const bool on = getenv("CE_VAE_DEBUG") != nullptr;
+    if (!on || dry || rc || !p) return;
+    unsigned long long* bad;
+    float* sum;
+    cudaMalloc(&bad, 8);
+    cudaMalloc(&sum, 4);
+    cudaMemsetAsync(bad, 0, 8, s);
+    cudaMemsetAsync(sum, 0, 4, s);
+    vae_debug_stats_kernel<<<256, 256, 0, s>>>(p, n, bad, sum);
+    unsigned long long hb = 0;
+    float hs = 0;
+    cudaMemcpyAsync(&hb, bad, 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&hs, sum, 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    printf("[vae-debug] %-44s n=%-10zu nonfinite=%-8llu mean|x|=%.5f %s\n", what.c_str(), n, hb, hs / (double)n, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    fflush(stdout);
+    cudaFree(bad);
+    cudaFree(sum);
+  }
 
   // ---- streaming conv input buffers
   StreamBuf& stream(const std::string& name, int hist, int tcap, int H, int W_, int C) {
@@ -138,6 +171,7 @@ struct Run {
     const bf16* g = W(gamma_name);
     if (dry || rc) return;
     ok(launch_rms_silu_cl(x.p, g, y, x.pixels(), x.C, silu ? 1 : 0, s));
+    debug("rms " + gamma_name, y, x.numel());
   }
   // implicit-GEMM conv reading `in` = [Tin frames] (history included) -> out
   void conv(const std::string& name, const bf16* in, int Tin, int Hin, int Win, int Cin, Act& out, int kt, int kh, int kw, int st, int sh,
@@ -153,6 +187,7 @@ struct Run {
     a.y = out.p; a.Tout = split_time ? out.T / 2 : out.T; a.Hout = out.H; a.Wout = out.W;
     a.resid = resid; a.split_time = split_time;
     ok(launch_conv3d_cl(a, s));
+    debug("conv " + name, out.p, out.numel());
   }
   // streaming causal conv (kt = 3): x is already in the stream buffer's chunk region
   void causal_conv(const std::string& name, StreamBuf& b, int T, Act& out, int kh, const bf16* resid = nullptr, int split_time = 0) {
@@ -167,6 +202,7 @@ struct Run {
     g.M = M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.out_f32 = out_f32; g.bias = bias; g.bias_row = bias_row;
     g.epi = epi; g.resid = resid; g.ldr = ldr;
     ok(launch_gemm_bf16(A, lda, Wt, ldw, g, s));
+    if (out) debug("gemm M=" + std::to_string(M) + " N=" + std::to_string(N) + " K=" + std::to_string(K), out, (size_t)M * ldo);
   }
 
   // ---- blocks

@@ -115,16 +115,14 @@ softmax_rows_kernel(const float* __restrict__ S, int lds, bf16* __restrict__ P, 
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
-  mx = warp_max(threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY);
-  mx = __shfl_sync(0xffffffffu, mx, 0);
+  mx = warp_max((threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : -INFINITY);
   __syncthreads();
   float sum = 0.f;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) sum += __expf((s[i] - mx) * scale);
   sum = warp_sum(sum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
-  sum = warp_sum(threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f);
-  sum = __shfl_sync(0xffffffffu, sum, 0);
+  sum = warp_sum((threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f);
   const float inv = 1.0f / sum;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) p[i] = __float2bfloat16_rn(__expf((s[i] - mx) * scale) * inv);
 }
