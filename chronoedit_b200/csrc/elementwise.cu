@@ -8,17 +8,7 @@ namespace ce {
 namespace {
 
 constexpr int ROW_THREADS = 256;
-constexpr int MAX_VEC_PER_THREAD = 4;  // 8 bf16 per vector -> D <= 256*4*8 = 8192
-
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();  // protect `red` against the previous use
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  float t = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.f;
-  return warp_sum(t);
-}
+constexpr int MAX_D = 8192;                // 32 lanes x 32 vectors x 8 bf16
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -29,46 +19,54 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// One WARP per token row (8 rows per CTA): every lane keeps VPL 16-byte vectors of the row in registers, so all of a
+// row's loads are in flight at once and the statistics need warp shuffles only (no shared memory, no __syncthreads).
+template <int VPL>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int D, float eps,
+layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
                  const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
                  const float* __restrict__ weight, const float* __restrict__ bias) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
-  float v[MAX_VEC_PER_THREAD][8];
+  uint4 v[VPL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
-    const int idx = threadIdx.x + i * ROW_THREADS;
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + i * 32;
     if (idx < nvec) {
-      unpack8(xr[idx], v[i]);
+      v[i] = xr[idx];
+      float f[8];
+      unpack8(v[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
+      for (int j = 0; j < 8; ++j) s += f[j];
     }
   }
-  const float mean = block_sum(s, red) / (float)D;
+  const float mean = warp_sum(s) / (float)D;
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
-    const int idx = threadIdx.x + i * ROW_THREADS;
-    if (idx < nvec) {
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + i * 32 < nvec) {
+      float f[8];
+      unpack8(v[i], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
+        const float d = f[j] - mean;
         ss += d * d;
       }
     }
   }
-  const float rstd = rsqrtf(block_sum(ss, red) / (float)D + eps);
+  const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
   const int b = row / rows_per_batch;
   uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
 #pragma unroll
-  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
-    const int idx = threadIdx.x + i * ROW_THREADS;
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + i * 32;
     if (idx < nvec) {
-      float o[8];
+      float f[8], o[8];
+      unpack8(v[i], f);
       const int c = idx * 8;
       if (scale) {
         const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c);
@@ -77,7 +75,7 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
         const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + scv[j]) + shv[j];
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * (1.0f + scv[j]) + shv[j];
       } else if (weight) {
         const float4* wp = reinterpret_cast<const float4*>(weight + c);
         const float4* bp = reinterpret_cast<const float4*>(bias + c);
@@ -85,10 +83,10 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * wv[j] + bv[j];
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd;
       }
       yr[idx] = pack8(o);
     }
@@ -96,37 +94,42 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+template <int VPL>
 __global__ void __launch_bounds__(ROW_THREADS)
-rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int D, float eps, const bf16* __restrict__ weight,
+rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int nvec = D >> 3;
   uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
-  float v[MAX_VEC_PER_THREAD][8];
+  uint4 v[VPL];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
-    const int idx = threadIdx.x + i * ROW_THREADS;
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + i * 32;
     if (idx < nvec) {
-      unpack8(xr[idx], v[i]);
+      v[i] = xr[idx];
+      float f[8];
+      unpack8(v[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
     }
   }
-  const float rstd = rsqrtf(block_sum(ss, red) / (float)D + eps);
+  const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
   const int tok = rope_cos ? row % L : 0;
   const int half = head_dim >> 1;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC_PER_THREAD; ++i) {
-    const int idx = threadIdx.x + i * ROW_THREADS;
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + i * 32;
     if (idx < nvec) {
-      float w[8], o[8];
+      float f[8], w[8], o[8];
+      unpack8(v[i], f);
       unpack8(wr[idx], w);
       // diffusers RMSNorm with a bf16 weight: (x * rstd) rounded to bf16, then * weight (bf16 multiply)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round(v[i][j] * rstd) * w[j]);
+      for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round(f[j] * rstd) * w[j]);
       if (rope_cos) {
         const int c = idx * 8;
         const int pair0 = (c % head_dim) >> 1;  // 4 consecutive (even, odd) pairs of one head
@@ -260,22 +263,36 @@ __global__ void add_table_kernel(const float* __restrict__ table, int table_rows
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
                      cudaStream_t stream) {
-  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= ROW_THREADS * MAX_VEC_PER_THREAD * 8, "layernorm: D must be a multiple of 8 and <= 8192");
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D, "layernorm: D must be a multiple of 8 and <= 8192");
   CE_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: leading dims % 8");
   CE_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale and shift come together");
   CE_REQUIRE((weight == nullptr) == (bias == nullptr), "layernorm: weight and bias come together");
   if (rows_per_batch <= 0) rows_per_batch = rows;
-  layernorm_kernel<<<rows, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias);
+  const int grid = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const int nvec = D / 8;
+#define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias)
+  if (nvec <= 128) CE_LN(4);
+  else if (nvec <= 256) CE_LN(8);
+  else if (nvec <= 640) CE_LN(20);
+  else CE_LN(32);
+#undef CE_LN
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }
 
 int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight, const float* rope_cos,
                         const float* rope_sin, int L, int head_dim, cudaStream_t stream) {
-  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= ROW_THREADS * MAX_VEC_PER_THREAD * 8, "rmsnorm: D must be a multiple of 8 and <= 8192");
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D, "rmsnorm: D must be a multiple of 8 and <= 8192");
   CE_REQUIRE(ldx % 8 == 0 && weight != nullptr, "rmsnorm: ldx % 8, weight");
   if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm: rope table / head_dim");
-  rmsnorm_rope_kernel<<<rows, ROW_THREADS, 0, stream>>>(x, ldx, D, eps, weight, rope_cos, rope_sin, L, head_dim);
+  const int grid = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const int nvec = D / 8;
+#define CE_RMS(V) rmsnorm_rope_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim)
+  if (nvec <= 128) CE_RMS(4);
+  else if (nvec <= 256) CE_RMS(8);
+  else if (nvec <= 640) CE_RMS(20);
+  else CE_RMS(32);
+#undef CE_RMS
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }
