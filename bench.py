@@ -322,6 +322,54 @@ def run_ours(args):
     e2e_steps = max(3, args.steps // 2)
     e2e_value = world * e2e_steps / (e2e_wall_ms / 1000.0)
 
+    # the VAE bookends of one edit (encode of the condition video, decode of the result), timed once per run
+    edit = None
+    if not args.no_vae:
+        from oracle import vae_oracle as V
+
+        vae = ce.AutoencoderKLWan(device=dev)
+        gv = torch.Generator(device=dev).manual_seed(7)
+        for n, p in vae.named_parameters():
+            if n.endswith("gamma"):
+                p.data.normal_(0, 0.1, generator=gv).add_(1.0)
+            elif n.endswith("bias"):
+                p.data.normal_(0, 0.02, generator=gv)
+            else:
+                fan_in = p[0].numel()
+                p.data.normal_(0, 1.0 / fan_in ** 0.5, generator=gv)
+        video = torch.zeros(1, 3, 5, 8 * LAT_H, 8 * LAT_W, dtype=torch.bfloat16, device=dev)
+        video[:, :, 0] = torch.rand(1, 3, 8 * LAT_H, 8 * LAT_W, device=dev) * 2 - 1
+        zlat = torch.randn(1, 16, FRAMES, LAT_H, LAT_W, dtype=torch.bfloat16, device=dev)
+
+        def time_once(fn, reps=2):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        enc_ms = time_once(lambda: vae.encode(video))
+        enc_launches = vae.launches()
+        dec_ms = time_once(lambda: vae.decode(zlat))
+        dec_launches = vae.launches()
+        cfgv = V.VAEConfig.wan21()
+        step_ms = dev_ms / args.steps
+        edit = {
+            "vae_encode_ms": enc_ms, "vae_decode_ms": dec_ms, "vae_encode_launches": enc_launches, "vae_decode_launches": dec_launches,
+            "vae_encode_conv_tflops": V.conv_flops(cfgv, 5, 8 * LAT_H, 8 * LAT_W, False) / enc_ms / 1e9,
+            "vae_decode_conv_tflops": V.conv_flops(cfgv, 5, 8 * LAT_H, 8 * LAT_W, True) / dec_ms / 1e9,
+            "vae_decode_algorithmic_GBps": 23.64e9 / dec_ms / 1e6,
+            "edits_per_sec_50_steps_all_gpus": world / ((enc_ms + dec_ms + 50 * step_ms) / 1000.0),
+            "edits_per_sec_8_steps_no_cfg_all_gpus": world / ((enc_ms + dec_ms + 8 * step_ms / 2) / 1000.0),
+            "note": "edit = VAE encode + N denoising steps + VAE decode (SURVEY 8d); text/image encoders excluded ('next' row)",
+        }
+        del vae
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         flops_fwd = O.flops_per_forward(O.DiTConfig(num_layers=args.layers), FRAMES, LAT_H, LAT_W, TEXT_LEN, 257, batch=2)
@@ -355,6 +403,7 @@ def run_ours(args):
             },
             "clocks": clocks,
             "weight_broadcast": {"bytes": bcast_bytes, "seconds_incl_init": round(t_bcast, 3)},
+            "edit": edit,
         }
         if world == 1 and not args.no_cpu_baseline:
             rate, times, cores, desc = cpu_reference_step_rate(reps=3, warmup=1)
@@ -372,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=40, help="DEV ONLY: fewer layers make the number invalid as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the (untimed-region) VAE encode/decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // One WARP per token row (8 rows per CTA): every lane keeps VPL 16-byte vectors of the row in registers, so all of a
 // row's loads are in flight at once and the statistics need warp shuffles only (no shared memory, no __syncthreads).
 template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
                  const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
                  const float* __restrict__ weight, const float* __restrict__ bias) {
@@ -32,7 +32,10 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
   uint4 v[VPL];
-  float s = 0.f;
+  // single statistics pass on pivot-shifted data d = x - x[row, 0] (no cancellation even when |mean| >> std):
+  //   mean = pivot + E[d],  var = E[d^2] - E[d]^2
+  const float pivot = __bfloat162float(x[(size_t)row * ldx]);
+  float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + i * 32;
@@ -41,24 +44,18 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
       float f[8];
       unpack8(v[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[j];
-    }
-  }
-  const float mean = warp_sum(s) / (float)D;
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    if (lane + i * 32 < nvec) {
-      float f[8];
-      unpack8(v[i], f);
-#pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = f[j] - mean;
-        ss += d * d;
+        const float d = f[j] - pivot;
+        s += d;
+        ss = fmaf(d, d, ss);
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float md = s / (float)D;
+  const float mean = pivot + md;
+  const float rstd = rsqrtf(fmaxf(ss / (float)D - md * md, 0.f) + eps);
   const int b = row / rows_per_batch;
   uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
 #pragma unroll
@@ -68,14 +65,17 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
       float f[8], o[8];
       unpack8(v[i], f);
       const int c = idx * 8;
-      if (scale) {
+      if (scale) {  // o = (x - mean) * rstd * (1 + scale) + shift  ==  x * a + (shift - mean * a),  a = rstd * (1 + scale)
         const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c);
         const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride + c);
         const float4 s0 = sc[0], s1 = sc[1], h0 = sh[0], h1 = sh[1];
         const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * (1.0f + scv[j]) + shv[j];
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaf(rstd, scv[j], rstd);
+          o[j] = fmaf(f[j], a, fmaf(-mean, a, shv[j]));
+        }
       } else if (weight) {
         const float4* wp = reinterpret_cast<const float4*>(weight + c);
         const float4* bp = reinterpret_cast<const float4*>(bias + c);
@@ -83,10 +83,14 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * wv[j] + bv[j];
+        for (int j = 0; j < 8; ++j) {
+          const float a = rstd * wv[j];
+          o[j] = fmaf(f[j], a, fmaf(-mean, a, bv[j]));
+        }
       } else {
+        const float nb = -mean * rstd;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd;
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], rstd, nb);
       }
       yr[idx] = pack8(o);
     }
@@ -95,7 +99,7 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
 
 // ---------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
   const int lane = threadIdx.x & 31;

@@ -13,6 +13,8 @@
 // Replaces the cuBLASLt calls behind every nn.Linear of the reference DiT block
 // (/root/reference/chronoedit_diffusers/transformer_chronoedit.py:58-60, 84-87, 106, 292) plus the elementwise
 // launches that follow them (:281, :286, :293).
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace ce {
@@ -253,6 +255,16 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 
 }  // namespace
 
+int launch_gemm_bf16_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream);  // gemm2.cu
+
+static bool use_2cta() {
+  static const bool on = [] {
+    const char* e = getenv("CE_GEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmArgs& g, cudaStream_t stream) {
   CE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem");
   CE_REQUIRE(g.N % 8 == 0, "gemm: N must be a multiple of 8");
@@ -269,8 +281,10 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)lda, BM);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, W, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)ldw, (uint32_t)bn);
+  const bool pair = bn == 256 && a.M >= 512 && use_2cta();  // 256 x 256 tiles on CTA pairs (gemm2.cu)
+  rc = make_tmap_2d(&tb, W, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)ldw, (uint32_t)(pair ? 128 : bn));
   if (rc) return rc;
+  if (pair) return launch_gemm_bf16_2cta(ta, tb, a, stream);
   if (bn == 256) return launch_variant<256, 4>(ta, tb, a, stream);
   if (bn == 128) return launch_variant<128, 6>(ta, tb, a, stream);
   return launch_variant<64, 8>(ta, tb, a, stream);

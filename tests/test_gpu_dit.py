@@ -103,3 +103,35 @@ def test_dit_rejects_bad_frames():
     x = torch.zeros(1, 36, 5, 8, 8)
     with pytest.raises(ce.CEError, match="num_frames must be 2 or"):
         m(x.cuda(), torch.tensor([1]).cuda(), torch.zeros(1, 512, 4096).cuda(), torch.zeros(1, 257, 1280).cuda())
+
+
+@gpu
+def test_dit_full_width_single_layer_at_720p():
+    """BASELINE.json configs[1] geometry at full 14B WIDTH (dim 5120, 40 heads, ffn 13824, 7200 tokens) with ONE block,
+    against the CPU oracle run here on the same seeded weights (fp32 = exact answer, bf16 = the reference's own path)."""
+    import chronoedit_b200 as ce
+    from oracle import cases, dit_oracle as O
+
+    cfg = O.DiTConfig(num_layers=1)
+    sd32 = O.random_state_dict(cfg, seed=3)
+    sdb = cases.to_bf16_state(sd32)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 36, 2, 90, 160, generator=g)
+    text = torch.randn(1, 512, 4096, generator=g)
+    text[:, 77:] = 0
+    img = torch.randn(1, 257, 1280, generator=g)
+    t = torch.tensor([601])
+    m = ce.ChronoEditTransformer3DModel(num_attention_heads=40, in_channels=36, out_channels=16, ffn_dim=13824, num_layers=1,
+                                        image_dim=1280, added_kv_proj_dim=5120)
+    m.load_state_dict(sdb)
+    m = m.cuda()
+    out = m(x.cuda(), t.cuda(), text.cuda(), img.cuda(), return_dict=False)[0].float().cpu()
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref32 = O.dit_forward(sd32, cfg, x, t, text, img)
+        ref16 = O.dit_forward(sdb, cfg, x.bfloat16(), t, text.bfloat16(), img.bfloat16()).float()
+    e_ref = (ref16 - ref32).abs()
+    e_our = (out - ref32).abs()
+    assert torch.isfinite(out).all()
+    assert e_our.mean() <= 1.25 * e_ref.mean(), f"mean err {e_our.mean():.3g} vs reference bf16 {e_ref.mean():.3g}"
+    assert e_our.max() <= 2.0 * e_ref.max(), f"max err {e_our.max():.3g} vs reference bf16 {e_ref.max():.3g}"
