@@ -63,6 +63,8 @@ SIGNATURES = {
                                c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ce_attention_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_float, c_int, c_void_p]),
+    "ce_attention_dual_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ce_layernorm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p]),
     "ce_rmsnorm_rope_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,

@@ -43,11 +43,12 @@ struct SmemLayout {
 };
 
 // barrier indices
-enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, PV_DONE = 13, NUM_BARS = 15 };
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, PV_DONE = 13, S_FREE = 15, NUM_BARS = 17 };
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                     const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
+                     const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_k2,
+                     const __grid_constant__ CUtensorMap tma_v2, AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
@@ -57,18 +58,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
+  // Key tiles are dealt to the two softmax groups g = 0, 1 as (g, t), t = 0..T[g]-1:
+  //   single source: tile index 2t + g of k/v (even / odd tiles), streams merged as ONE softmax at the end;
+  //   dual source  : group 0 walks k/v (Lk keys), group 1 walks k2/v2 (Lk2 keys); the two attention results are summed.
+  const bool dual = a.Lk2 > 0;
   const int n_tiles = (a.Lk + BKV - 1) / BKV;
+  const int T0 = dual ? n_tiles : (n_tiles + 1) / 2;
+  const int T1 = dual ? (a.Lk2 + BKV - 1) / BKV : n_tiles / 2;
+  const int Tmax = T0 > T1 ? T0 : T1;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
       printf("[chronoedit_b200] attention: dynamic shared memory not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < NUM_BARS; ++i) mbar_init(&bars[i], (i == P_FULL || i == P_FULL + 1) ? 128 : 1);
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(&bars[i], (i == P_FULL || i == P_FULL + 1 || i == S_FREE || i == S_FREE + 1) ? 128 : 1);
     fence_mbar_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_k2);
+    tma_prefetch_desc(&tma_v2);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -85,19 +95,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       mbar_arrive_expect_tx(&bars[Q_FULL], TILE_BYTES);
       tma_load_3d(smem + SmemLayout::q, &tma_q, &bars[Q_FULL], h * HD, q0, b);
       tma_load_3d(smem + SmemLayout::q + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        uint8_t* ks = smem + SmemLayout::k + st * TILE_BYTES;
-        uint8_t* vs = smem + SmemLayout::v + st * TILE_BYTES;
-        mbar_wait(&bars[K_EMPTY + st], ph ^ 1, 10 + st);
-        mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
-        tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, j * BKV, b);
-        tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, j * BKV, b);
-        mbar_wait(&bars[V_EMPTY + st], ph ^ 1, 20 + st);
-        mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
-        tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, j * BKV, b);
-        tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, j * BKV, b);
+      for (int t = 0; t < Tmax; ++t) {
+        for (int g = 0; g < 2; ++g) {
+          if (t >= (g ? T1 : T0)) continue;
+          const int row0 = (dual ? t : 2 * t + g) * BKV;
+          const CUtensorMap* mk = (dual && g) ? &tma_k2 : &tma_k;
+          const CUtensorMap* mv = (dual && g) ? &tma_v2 : &tma_v;
+          const uint32_t ph = t & 1;
+          uint8_t* ks = smem + SmemLayout::k + g * TILE_BYTES;
+          uint8_t* vs = smem + SmemLayout::v + g * TILE_BYTES;
+          mbar_wait(&bars[K_EMPTY + g], ph ^ 1, 10 + g);
+          mbar_arrive_expect_tx(&bars[K_FULL + g], TILE_BYTES);
+          tma_load_3d(ks, mk, &bars[K_FULL + g], h * HD, row0, b);
+          tma_load_3d(ks + HALF_BYTES, mk, &bars[K_FULL + g], h * HD + 64, row0, b);
+          mbar_wait(&bars[V_EMPTY + g], ph ^ 1, 20 + g);
+          mbar_arrive_expect_tx(&bars[V_FULL + g], TILE_BYTES);
+          tma_load_3d(vs, mv, &bars[V_FULL + g], h * HD, row0, b);
+          tma_load_3d(vs + HALF_BYTES, mv, &bars[V_FULL + g], h * HD + 64, row0, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -106,41 +121,48 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major) x K^T (K-major)
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (K-major) x V (MN-major)
       const uint32_t q_addr = smem_u32(smem + SmemLayout::q);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&bars[K_FULL + st], (j >> 1) & 1, 30 + st);
+      auto issue_s = [&](int g, int t) {
+        mbar_wait(&bars[K_FULL + g], t & 1, 30 + g);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + SmemLayout::k + st * TILE_BYTES);
-        const uint32_t d = tmem_base + (j & 1) * 128;
+        const uint32_t k_addr = smem_u32(smem + SmemLayout::k + g * TILE_BYTES);
+        const uint32_t d = tmem_base + g * 128;
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t off = (kk >> 2) * HALF_BYTES;
           umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3),
                        umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S, kk != 0);
         }
-        umma_commit(&bars[K_EMPTY + st]);
-        umma_commit(&bars[S_FULL + (j & 1)]);
+        umma_commit(&bars[K_EMPTY + g]);
+        umma_commit(&bars[S_FULL + g]);
       };
       mbar_wait(&bars[Q_FULL], 0, 1);
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        const int g = j & 1;
-        const int t = j >> 1;
-        mbar_wait(&bars[P_FULL + g], t & 1, 40 + g);
-        mbar_wait(&bars[V_FULL + g], t & 1, 50 + g);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
-        const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
-        const uint32_t d = tmem_base + 256 + g * 128;
+      issue_s(0, 0);
+      if (T1 > 0) issue_s(1, 0);
+      for (int t = 0; t < Tmax; ++t) {
+        for (int g = 0; g < 2; ++g) {
+          const int Tg = g ? T1 : T0;
+          if (t >= Tg) continue;
+          if (t + 1 < Tg) {
+            // the softmax group has pulled S(g,t) into registers: its TMEM buffer can take S(g,t+1) while exp / P are computed
+            mbar_wait(&bars[S_FREE + g], t & 1, 35 + g);
+            tc_fence_after();
+            issue_s(g, t + 1);
+          }
+          mbar_wait(&bars[P_FULL + g], t & 1, 40 + g);
+          mbar_wait(&bars[V_FULL + g], t & 1, 50 + g);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
+          const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
+          const uint32_t d = tmem_base + 256 + g * 128;
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
-          umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+            const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
+            umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
+          }
+          umma_commit(&bars[V_EMPTY + g]);
+          umma_commit(&bars[PV_DONE + g]);
         }
-        umma_commit(&bars[V_EMPTY + g]);
-        umma_commit(&bars[PV_DONE + g]);
       }
     }
   }
@@ -155,12 +177,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const uint32_t o_tmem = tmem_base + lane_base + 256 + g * 128;
     uint8_t* p_smem = smem + SmemLayout::p + g * TILE_BYTES;
     const float sl2 = a.scale * 1.4426950408889634f;
-    const int my_tiles = (n_tiles - g + 1) / 2;
+    const int my_tiles = g ? T1 : T0;
+    const int my_len = (dual && g) ? a.Lk2 : a.Lk;
     float m = -INFINITY, l = 0.f;
 
     for (int t = 0; t < my_tiles; ++t) {
-      const int j = 2 * t + g;
-      const int valid = a.Lk - j * BKV;  // >= 1; >= 128 means no masking
+      const int valid = my_len - (dual ? t : 2 * t + g) * BKV;  // >= 1; >= 128 means no masking
       mbar_wait(&bars[S_FULL + g], t & 1, 60 + g);
       tc_fence_after();
       // the whole 128-wide score row of this thread goes to registers with one wait (4 x tcgen05.ld in flight)
@@ -168,6 +190,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[S_FREE + g]);  // S buffer drained
       if (valid < BKV) {  // last key tile only (warp-uniform): masked scores -> -inf -> p = 0
 #pragma unroll
         for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
@@ -241,12 +265,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const float2 other = reinterpret_cast<const float2*>(smem + SmemLayout::p + (g ^ 1) * TILE_BYTES)[r];
     const float m_e = g == 0 ? m : other.x, l_e = g == 0 ? l : other.y;
     const float m_o = g == 0 ? other.x : m, l_o = g == 0 ? other.y : l;
-    const bool has_o = n_tiles > 1;
-    const float mm = has_o ? fmaxf(m_e, m_o) : m_e;
-    const float a_e = fast_exp2(m_e - mm);
-    const float a_o = has_o ? fast_exp2(m_o - mm) : 0.f;
-    const float inv = 1.0f / (l_e * a_e + l_o * a_o);
-    const float w_e = a_e * inv, w_o = a_o * inv;
+    const bool has_o = T1 > 0;
+    float w_e, w_o;
+    if (dual) {  // two separate softmaxes (text keys, image keys): each normalised on its own, results added (:103-104)
+      w_e = 1.0f / l_e;
+      w_o = has_o ? 1.0f / l_o : 0.f;
+    } else {
+      const float mm = has_o ? fmaxf(m_e, m_o) : m_e;
+      const float a_e = fast_exp2(m_e - mm);
+      const float a_o = has_o ? fast_exp2(m_o - mm) : 0.f;
+      const float inv = 1.0f / (l_e * a_e + l_o * a_o);
+      w_e = a_e * inv;
+      w_o = a_o * inv;
+    }
     const int row = q0 + r;
     bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD + g * 64;
     const uint32_t oe_tmem = tmem_base + lane_base + 256 + g * 64;
@@ -264,7 +295,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             y[i] = __uint_as_float(oe[v4 * 8 + i]) * w_e;
-            if (has_o) y[i] += __uint_as_float(oo[v4 * 8 + i]) * w_o;
+            if (dual) {  // each SDPA result is a bf16 tensor in the reference before the add
+              y[i] = bf16_round(y[i]);
+              if (has_o) y[i] += bf16_round(__uint_as_float(oo[v4 * 8 + i]) * w_o);
+            } else if (has_o) {
+              y[i] += __uint_as_float(oo[v4 * 8 + i]) * w_o;
+            }
           }
           uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8);
           if (a.accumulate) {
@@ -301,11 +337,19 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
   CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, tk2, tv2;
   int rc;
   if ((rc = make_qkv_tmap(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
+  if (a.Lk2 > 0) {
+    CE_REQUIRE(a.k2 && a.v2 && a.ldk2 % 8 == 0 && a.ldv2 % 8 == 0, "attention: dual source needs k2 / v2");
+    if ((rc = make_qkv_tmap(&tk2, a.k2, a.B, a.Lk2, a.H, a.ldk2))) return rc;
+    if ((rc = make_qkv_tmap(&tv2, a.v2, a.B, a.Lk2, a.H, a.ldv2))) return rc;
+  } else {
+    tk2 = tk;
+    tv2 = tv;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CE_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -313,7 +357,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.Lq + BQ - 1) / BQ, a.H, a.B);
-  attention_fwd_kernel<<<grid, ATTN_THREADS, SmemLayout::total, stream>>>(tq, tk, tv, a);
+  attention_fwd_kernel<<<grid, ATTN_THREADS, SmemLayout::total, stream>>>(tq, tk, tv, tk2, tv2, a);
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -13,6 +13,13 @@ struct AttnArgs {
   int ldk = 0;
   const bf16* v = nullptr;
   int ldv = 0;
+  // optional SECOND key/value source (Lk2 > 0): out = bf16(attn(q,k,v)) + bf16(attn(q,k2,v2)), two independent softmaxes
+  // in ONE launch (text + image cross-attention, transformer_chronoedit.py:84-104)
+  const bf16* k2 = nullptr;
+  int ldk2 = 0;
+  const bf16* v2 = nullptr;
+  int ldv2 = 0;
+  int Lk2 = 0;
   bf16* out = nullptr;      // out[b, i, h*hd + d]
   int ldo = 0;
   float scale = 0.f;        // 1/sqrt(head_dim)

@@ -295,7 +295,7 @@ static int linear(ce_dit* h, const bf16* A, int lda, const std::string& wname, i
   return rc;
 }
 static int attention(ce_dit* h, const AttnArgs& a, cudaStream_t s) {
-  prof_begin(h, CAT_ATTN, 4.0 * a.B * a.H * (double)a.Lq * a.Lk * a.head_dim, s);
+  prof_begin(h, CAT_ATTN, 4.0 * a.B * a.H * (double)a.Lq * (a.Lk + a.Lk2) * a.head_dim, s);
   int rc = launch_attention(a, s);
   if (rc == 0) prof_end(h, s);
   return rc;
@@ -436,8 +436,8 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
                           ws.temb_f32, ws.temb_bf16, s));  // temb = (...).type_as(bf16)
   RUN(launch_small_linear(ws.temb_f32, D, W_BF16(ce_ + "time_proj.weight"), W_BF16(ce_ + "time_proj.bias"), 1, 6 * D, B, 0, /*in_silu_bf16=*/1,
                           nullptr, ws.tproj, s));
-  RUN(launch_add_table(W_F32("blocks.scale_shift_table"), c.num_layers, ws.tproj, 6 * D, ws.mod, B, D, 6, s));
-  RUN(launch_add_table(W_F32("scale_shift_table"), 1, ws.temb_bf16, D, ws.modf, B, D, 2, s));
+  RUN(launch_add_table(W_F32("blocks.scale_shift_table"), c.num_layers, ws.tproj, 6 * D, ws.mod, B, D, 6, s, /*scale chunks 1,4 -> 1+scale*/ 0x12u));
+  RUN(launch_add_table(W_F32("scale_shift_table"), 1, ws.temb_bf16, D, ws.modf, B, D, 2, s, /*chunk 1 = scale*/ 0x2u));
   // text: Linear -> GELU(tanh) -> Linear
   RUN2(linear(h, reinterpret_cast<const bf16*>(encoder_hidden_states), c.text_dim, ce_ + "text_embedder.linear_1", B * Lt, D, c.text_dim,
              ws.text1, D, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
@@ -457,7 +457,7 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     const std::string p = "blocks." + std::to_string(i) + ".";
     const float* mod = ws.mod + (size_t)i * B * 6 * D;  // [B, 6, D]: shift, scale, gate, c_shift, c_scale, c_gate
     // 1. self-attention
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, s, 1));
     RUN2(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
     RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
     RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv + D, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_k.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
@@ -479,32 +479,28 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
     RUN2(linear(h, ws.ctx_text, D, p + "attn2.to_kv", B * Lt, 2 * D, D, ws.kv_text, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
     RUN(launch_rmsnorm_rope(ws.kv_text, 2 * D, B * Lt, D, c.eps, W_BF16(p + "attn2.norm_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
-    {
+    if (c.image_dim > 0) {
+      RUN2(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, ws.kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+      RUN(launch_rmsnorm_rope(ws.kv_img, 2 * D, B * Li, D, c.eps, W_BF16(p + "attn2.norm_added_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+    }
+    {  // text and image cross-attention in ONE launch: two key/value sources, two softmaxes, results added (:84-104)
       AttnArgs a;
       a.B = B; a.H = H; a.Lq = L; a.Lk = Lt;
       a.q = q2; a.ldq = D;
       a.k = ws.kv_text; a.ldk = 2 * D;
       a.v = ws.kv_text + D; a.ldv = 2 * D;
+      if (c.image_dim > 0) {
+        a.k2 = ws.kv_img; a.ldk2 = 2 * D;
+        a.v2 = ws.kv_img + D; a.ldv2 = 2 * D;
+        a.Lk2 = Li;
+      }
       a.out = ws.attn; a.ldo = D;
       a.scale = attn_scale;
-      RUN2(attention(h, a, s));
-    }
-    if (c.image_dim > 0) {
-      RUN2(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, ws.kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-      RUN(launch_rmsnorm_rope(ws.kv_img, 2 * D, B * Li, D, c.eps, W_BF16(p + "attn2.norm_added_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
-      AttnArgs a;
-      a.B = B; a.H = H; a.Lq = L; a.Lk = Li;
-      a.q = q2; a.ldq = D;
-      a.k = ws.kv_img; a.ldk = 2 * D;
-      a.v = ws.kv_img + D; a.ldv = 2 * D;
-      a.out = ws.attn; a.ldo = D;
-      a.scale = attn_scale;
-      a.accumulate = 1;
       RUN2(attention(h, a, s));
     }
     RUN2(linear(h, ws.attn, D, p + "attn2.to_out.0", M, D, D, ws.x, D, EPI_BIAS_RESID, ws.x, D, nullptr, 0, 1, s));
     // 3. feed-forward
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, s, 1));
     RUN2(linear(h, ws.xn, D, p + "ffn.net.0.proj", M, F, D, ws.hbuf, F, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
     RUN2(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s));
     if (i == 0 && block0_out)
@@ -512,7 +508,7 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
   }
 
   // ---- output head (:451-467): modf = [B, 2, D] with shift = chunk 0, scale = chunk 1
-  RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, s));
+  RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, s, 1));
   RUN2(linear(h, ws.xn, D, "proj_out", M, No, D, ws.yout, No, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
   RUN(launch_unpatchify(ws.yout, No, reinterpret_cast<bf16*>(sample), B, c.out_channels, frames, height, width, s));
   return CE_OK;
@@ -589,6 +585,22 @@ int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void
   a.out = reinterpret_cast<bf16*>(out); a.ldo = ldo;
   a.scale = scale;
   a.accumulate = accumulate;
+  return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ce_attention_dual_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* k2, int ldk2, const void* v2,
+                           int ldv2, void* out, int ldo, int B, int H, int Lq, int Lk, int Lk2, float scale, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  AttnArgs a;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.Lk2 = Lk2;
+  a.q = reinterpret_cast<const bf16*>(q); a.ldq = ldq;
+  a.k = reinterpret_cast<const bf16*>(k); a.ldk = ldk;
+  a.v = reinterpret_cast<const bf16*>(v); a.ldv = ldv;
+  a.k2 = reinterpret_cast<const bf16*>(k2); a.ldk2 = ldk2;
+  a.v2 = reinterpret_cast<const bf16*>(v2); a.ldv2 = ldv2;
+  a.out = reinterpret_cast<bf16*>(out); a.ldo = ldo;
+  a.scale = scale;
   return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

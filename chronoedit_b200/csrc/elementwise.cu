@@ -22,25 +22,29 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // One WARP per token row (8 rows per CTA): every lane keeps VPL 16-byte vectors of the row in registers, so all of a
 // row's loads are in flight at once and the statistics need warp shuffles only (no shared memory, no __syncthreads).
 template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
+__global__ void __launch_bounds__(ROW_THREADS)
 layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
                  const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
-                 const float* __restrict__ weight, const float* __restrict__ bias) {
+                 const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
   uint4 v[VPL];
+  // all of the row's loads are issued before anything consumes them
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + i * 32;
+    v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
+  }
   // single statistics pass on pivot-shifted data d = x - x[row, 0] (no cancellation even when |mean| >> std):
   //   mean = pivot + E[d],  var = E[d^2] - E[d]^2
   const float pivot = __bfloat162float(x[(size_t)row * ldx]);
   float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nvec) {
-      v[i] = xr[idx];
+    if (lane + i * 32 < nvec) {
       float f[8];
       unpack8(v[i], f);
 #pragma unroll
@@ -56,50 +60,55 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
   const float md = s / (float)D;
   const float mean = pivot + md;
   const float rstd = rsqrtf(fmaxf(ss / (float)D - md * md, 0.f) + eps);
+  const float nmr = -mean * rstd;
   const int b = row / rows_per_batch;
   uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
+  const float* pa = scale ? scale + (size_t)b * mod_stride : weight;  // multiplier table: (1 + scale) or scale, or the affine weight
+  const float* pb = scale ? shift + (size_t)b * mod_stride : bias;
+  constexpr int G = 4;  // vectors per batch: their 4 x 4 parameter loads are in flight together
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nvec) {
-      float f[8], o[8];
-      unpack8(v[i], f);
-      const int c = idx * 8;
-      if (scale) {  // o = (x - mean) * rstd * (1 + scale) + shift  ==  x * a + (shift - mean * a),  a = rstd * (1 + scale)
-        const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c);
-        const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride + c);
-        const float4 s0 = sc[0], s1 = sc[1], h0 = sh[0], h1 = sh[1];
-        const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  for (int i0 = 0; i0 < VPL; i0 += G) {
+    float4 ta[G][2], tb[G][2];
+    if (pa) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = fmaf(rstd, scv[j], rstd);
-          o[j] = fmaf(f[j], a, fmaf(-mean, a, shv[j]));
+      for (int k = 0; k < G; ++k) {
+        const int idx = lane + (i0 + k) * 32;
+        if (i0 + k < VPL && idx < nvec) {
+          const float4* qa = reinterpret_cast<const float4*>(pa + idx * 8);
+          const float4* qb = reinterpret_cast<const float4*>(pb + idx * 8);
+          ta[k][0] = qa[0]; ta[k][1] = qa[1];
+          tb[k][0] = qb[0]; tb[k][1] = qb[1];
         }
-      } else if (weight) {
-        const float4* wp = reinterpret_cast<const float4*>(weight + c);
-        const float4* bp = reinterpret_cast<const float4*>(bias + c);
-        const float4 w0 = wp[0], w1 = wp[1], b0 = bp[0], b1 = bp[1];
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = rstd * wv[j];
-          o[j] = fmaf(f[j], a, fmaf(-mean, a, bv[j]));
-        }
-      } else {
-        const float nb = -mean * rstd;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], rstd, nb);
       }
-      yr[idx] = pack8(o);
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int idx = lane + (i0 + k) * 32;
+      if (i0 + k < VPL && idx < nvec) {
+        float f[8], o[8];
+        unpack8(v[i0 + k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], rstd, nmr);  // (x - mean) * rstd
+        if (pa) {
+          const float av[8] = {ta[k][0].x, ta[k][0].y, ta[k][0].z, ta[k][0].w, ta[k][1].x, ta[k][1].y, ta[k][1].z, ta[k][1].w};
+          const float bv[8] = {tb[k][0].x, tb[k][0].y, tb[k][0].z, tb[k][0].w, tb[k][1].x, tb[k][1].y, tb[k][1].z, tb[k][1].w};
+          if (scale && !scale_is_1p) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], 1.0f + av[j], bv[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], av[j], bv[j]);
+          }
+        }
+        yr[idx] = pack8(o);
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
+__global__ void __launch_bounds__(ROW_THREADS)
 rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
   const int lane = threadIdx.x & 31;
@@ -109,17 +118,18 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, c
   uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
   uint4 v[VPL];
-  float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + i * 32;
-    if (idx < nvec) {
-      v[i] = xr[idx];
-      float f[8];
-      unpack8(v[i], f);
+    v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
-    }
+  for (int i = 0; i < VPL; ++i) {
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
   }
   const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
   const int tok = rope_cos ? row % L : 0;
@@ -249,7 +259,7 @@ __global__ void timestep_sinusoid_kernel(const float* __restrict__ t, float* __r
 }
 
 __global__ void add_table_kernel(const float* __restrict__ table, int table_rows, const bf16* __restrict__ src, int src_ld,
-                                 int src_per_chunk, float* __restrict__ dst, int B, int n, int chunks) {
+                                 int src_per_chunk, float* __restrict__ dst, int B, int n, int chunks, unsigned plus_one_mask) {
   // dst[l, b, c, d] = table[l, c, d] + float(src[b, (src_per_chunk ? c*n : 0) + d])
   const size_t total = (size_t)table_rows * B * chunks * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -258,7 +268,8 @@ __global__ void add_table_kernel(const float* __restrict__ table, int table_rows
     const int c = (int)(r % chunks); r /= chunks;
     const int b = (int)(r % B);
     const int l = (int)(r / B);
-    dst[i] = table[((size_t)l * chunks + c) * n + d] + __bfloat162float(src[(size_t)b * src_ld + (src_per_chunk ? c * n : 0) + d]);
+    const float v = table[((size_t)l * chunks + c) * n + d] + __bfloat162float(src[(size_t)b * src_ld + (src_per_chunk ? c * n : 0) + d]);
+    dst[i] = ((plus_one_mask >> c) & 1u) ? 1.0f + v : v;  // "scale" chunks are stored as (1 + scale)
   }
 }
 
@@ -266,7 +277,7 @@ __global__ void add_table_kernel(const float* __restrict__ table, int table_rows
 
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int scale_is_1p) {
   CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D, "layernorm: D must be a multiple of 8 and <= 8192");
   CE_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: leading dims % 8");
   CE_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale and shift come together");
@@ -274,7 +285,7 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, 
   if (rows_per_batch <= 0) rows_per_batch = rows;
   const int grid = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
   const int nvec = D / 8;
-#define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias)
+#define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p)
   if (nvec <= 128) CE_LN(4);
   else if (nvec <= 256) CE_LN(8);
   else if (nvec <= 640) CE_LN(20);
@@ -339,11 +350,11 @@ int launch_timestep_sinusoid(const float* t, float* emb, int B, int dim, cudaStr
 }
 
 int launch_add_table(const float* table, int table_rows, const bf16* src, int src_ld, float* dst, int B, int n,
-                     int chunks, cudaStream_t stream) {
+                     int chunks, cudaStream_t stream, unsigned plus_one_mask) {
   const size_t total = (size_t)table_rows * B * chunks * n;
   const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   const int src_per_chunk = src_ld >= chunks * n ? 1 : 0;
-  add_table_kernel<<<grid, 256, 0, stream>>>(table, table_rows, src, src_ld, src_per_chunk, dst, B, n, chunks);
+  add_table_kernel<<<grid, 256, 0, stream>>>(table, table_rows, src, src_ld, src_per_chunk, dst, B, n, chunks, plus_one_mask);
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -8,9 +8,10 @@ namespace ce {
 // y[row, :] = bf16( LN_fp32(x[row, :]) * (1 + scale[b, :]) + shift[b, :] )     (b = row / rows_per_batch)
 //   scale/shift: fp32 [batches, mod_stride] or null (then the optional affine weight/bias, fp32 [D], is applied)
 // FP32LayerNorm + adaLN modulate of transformer_chronoedit.py:279, 289, 460 and the affine norm2 of :284.
+//   scale_is_1p: the `scale` table already holds (1 + scale) (ce_dit stores its modulation tables that way)
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int scale_is_1p = 0);
 
 // In place on x[rows, D] (leading dim ldx): diffusers RMSNorm across all heads (fp32 variance over D,
 // y = bf16(bf16(x * rstd) * w)), then optionally interleaved-pair RoPE with cos/sin tables [L, hd/2] fp32
@@ -35,7 +36,8 @@ int launch_small_linear(const float* x, int K, const void* W, const void* bias, 
 int launch_timestep_sinusoid(const float* t, float* emb, int B, int dim, cudaStream_t stream);
 
 // dst[b, :] = table[b % table_rows, :] + src[b, :] (fp32): scale_shift_table + temb (:274-276, :451)
+//   plus_one_mask: bit c set -> chunk c is stored as 1 + value (the adaLN "scale" chunks)
 int launch_add_table(const float* table, int table_rows, const bf16* src, int src_ld, float* dst, int B, int n,
-                     int chunks, cudaStream_t stream);
+                     int chunks, cudaStream_t stream, unsigned plus_one_mask = 0);
 
 }  // namespace ce

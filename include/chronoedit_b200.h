@@ -162,6 +162,12 @@ int ce_linear_bf16(const void* A, int lda, const void* W, int ldw, const void* b
 int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                       int H, int Lq, int Lk, float scale, int accumulate, void* stream);
 
+/* Cross-attention with TWO key/value sources in one launch: out = bf16(SDPA(q,k,v)) + bf16(SDPA(q,k2,v2)) — the text and
+ * image streams of ChronoEditAttnProcessor2_0 (transformer_chronoedit.py:84-104). */
+int ce_attention_dual_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* k2, int ldk2,
+                           const void* v2, int ldv2, void* out, int ldo, int B, int H, int Lq, int Lk, int Lk2, float scale,
+                           void* stream);
+
 /* FP32LayerNorm (+ adaLN modulate or affine) over the last dim of x[rows, D] -> y (bf16). (:279, :284, :289, :460) */
 int ce_layernorm_bf16(const void* x, int ldx, void* y, int ldy, int rows, int D, float eps, const float* scale,
                       const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,

@@ -1,0 +1,9 @@
+#!/bin/bash
+TAG=${1:-r01e}
+mkdir -p gpurun_out
+echo "=== tests" | tee gpurun_out/tests_${TAG}.log
+timeout 1500 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -15 | tee -a gpurun_out/tests_${TAG}.log
+echo "=== ops" | tee gpurun_out/ops_${TAG}.log
+timeout 600 python scripts/bench_ops.py attn rows 2>&1 | tee -a gpurun_out/ops_${TAG}.log
+echo "=== bench"; timeout 1500 python bench.py --steps 6 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_${TAG}.log
+echo "=== reference arm"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref_${TAG}.log

@@ -235,3 +235,31 @@ def test_rmsnorm_rope(rows, H, rope):
         yh = O._apply_rope(yh, O.rope_table(cfg, frames, hp * 2, wp * 2))
         y = yh.transpose(1, 2).flatten(2, 3)
     _bf16_close(buf[:, D:2 * D], y[0].float(), f"rmsnorm_rope rows={rows} H={H} rope={rope}")
+
+
+@gpu
+@pytest.mark.parametrize("Lq,Lk,Lk2", [(300, 512, 257), (7200, 512, 257), (130, 7, 300)])
+def test_attention_dual_source(Lq, Lk, Lk2):
+    """text + image cross-attention in one launch == sum of two separate bf16 SDPAs (transformer_chronoedit.py:84-104)."""
+    L = _lib()
+    lib = L.lib()
+    B, H, hd = 2, 2, 128
+    D = H * hd
+    g = torch.Generator(device="cpu").manual_seed(Lq + Lk2)
+    q = torch.randn(B, Lq, D, generator=g).bfloat16().cuda()
+    kv = torch.randn(B, Lk, 2 * D, generator=g).bfloat16().cuda()
+    kv2 = torch.randn(B, Lk2, 2 * D, generator=g).bfloat16().cuda()
+    out = torch.zeros(B, Lq, D, dtype=torch.bfloat16, device="cuda")
+    scale = 1.0 / math.sqrt(hd)
+    L.check(lib.ce_attention_dual_bf16(L.ptr(q), D, L.ptr(kv), 2 * D, L.ptr(kv[..., D:]), 2 * D, L.ptr(kv2), 2 * D, L.ptr(kv2[..., D:]), 2 * D,
+                                       L.ptr(out), D, B, H, Lq, Lk, Lk2, scale, L.current_stream()))
+    torch.cuda.synchronize()
+
+    def sdpa(k, v, n):
+        qf = q.float().reshape(B, Lq, H, hd).transpose(1, 2)
+        kf = k.float().reshape(B, n, H, hd).transpose(1, 2)
+        vf = v.float().reshape(B, n, H, hd).transpose(1, 2)
+        return (torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf).transpose(1, 2).reshape(B, Lq, D)
+
+    ref = sdpa(kv[..., :D], kv[..., D:], Lk).bfloat16().float() + sdpa(kv2[..., :D], kv2[..., D:], Lk2).bfloat16().float()
+    _bf16_close(out, ref, f"dual attention Lq={Lq} Lk={Lk} Lk2={Lk2}", ulp=2.0, mean_tol=4e-3)
