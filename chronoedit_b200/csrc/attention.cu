@@ -88,30 +88,54 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 
   // register re-partition (warpgroup-aligned): the producer / MMA warpgroup gives its registers to the softmax warpgroups
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars[Q_FULL], TILE_BYTES);
       tma_load_3d(smem + SmemLayout::q, &tma_q, &bars[Q_FULL], h * HD, q0, b);
       tma_load_3d(smem + SmemLayout::q + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0, b);
-      for (int t = 0; t < Tmax; ++t) {
+      // Event-driven: each (group, K|V) stream advances as soon as ITS slot is free, so a K load never queues behind a V wait.
+      int k_next[2] = {0, 0}, v_next[2] = {0, 0};
+      const int T[2] = {T0, T1};
+      uint64_t t_start = 0;
+      uint32_t idle = 0;
+      while (k_next[0] < T0 || k_next[1] < T1 || v_next[0] < T0 || v_next[1] < T1) {
+        bool progress = false;
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (t >= (g ? T1 : T0)) continue;
-          const int row0 = (dual ? t : 2 * t + g) * BKV;
           const CUtensorMap* mk = (dual && g) ? &tma_k2 : &tma_k;
           const CUtensorMap* mv = (dual && g) ? &tma_v2 : &tma_v;
-          const uint32_t ph = t & 1;
-          uint8_t* ks = smem + SmemLayout::k + g * TILE_BYTES;
-          uint8_t* vs = smem + SmemLayout::v + g * TILE_BYTES;
-          mbar_wait(&bars[K_EMPTY + g], ph ^ 1, 10 + g);
-          mbar_arrive_expect_tx(&bars[K_FULL + g], TILE_BYTES);
-          tma_load_3d(ks, mk, &bars[K_FULL + g], h * HD, row0, b);
-          tma_load_3d(ks + HALF_BYTES, mk, &bars[K_FULL + g], h * HD + 64, row0, b);
-          mbar_wait(&bars[V_EMPTY + g], ph ^ 1, 20 + g);
-          mbar_arrive_expect_tx(&bars[V_FULL + g], TILE_BYTES);
-          tma_load_3d(vs, mv, &bars[V_FULL + g], h * HD, row0, b);
-          tma_load_3d(vs + HALF_BYTES, mv, &bars[V_FULL + g], h * HD + 64, row0, b);
+          int t = k_next[g];
+          if (t < T[g] && mbar_try_wait(&bars[K_EMPTY + g], (t & 1) ^ 1)) {
+            const int row0 = (dual ? t : 2 * t + g) * BKV;
+            uint8_t* ks = smem + SmemLayout::k + g * TILE_BYTES;
+            mbar_arrive_expect_tx(&bars[K_FULL + g], TILE_BYTES);
+            tma_load_3d(ks, mk, &bars[K_FULL + g], h * HD, row0, b);
+            tma_load_3d(ks + HALF_BYTES, mk, &bars[K_FULL + g], h * HD + 64, row0, b);
+            ++k_next[g];
+            progress = true;
+          }
+          t = v_next[g];
+          if (t < T[g] && mbar_try_wait(&bars[V_EMPTY + g], (t & 1) ^ 1)) {
+            const int row0 = (dual ? t : 2 * t + g) * BKV;
+            uint8_t* vs = smem + SmemLayout::v + g * TILE_BYTES;
+            mbar_arrive_expect_tx(&bars[V_FULL + g], TILE_BYTES);
+            tma_load_3d(vs, mv, &bars[V_FULL + g], h * HD, row0, b);
+            tma_load_3d(vs + HALF_BYTES, mv, &bars[V_FULL + g], h * HD + 64, row0, b);
+            ++v_next[g];
+            progress = true;
+          }
+        }
+        if (progress) {
+          idle = 0;
+        } else if ((++idle & 0xFFF) == 0) {
+          if (t_start == 0) t_start = global_timer_ns();
+          else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
+            printf("[chronoedit_b200] attention producer stalled: block=(%d,%d,%d) k=%d,%d v=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   k_next[0], k_next[1], v_next[0], v_next[1]);
+            __trap();
+          }
         }
       }
     }
@@ -135,33 +159,54 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         umma_commit(&bars[K_EMPTY + g]);
         umma_commit(&bars[S_FULL + g]);
       };
-      mbar_wait(&bars[Q_FULL], 0, 1);
-      issue_s(0, 0);
-      if (T1 > 0) issue_s(1, 0);
-      for (int t = 0; t < Tmax; ++t) {
-        for (int g = 0; g < 2; ++g) {
-          const int Tg = g ? T1 : T0;
-          if (t >= Tg) continue;
-          if (t + 1 < Tg) {
-            // the softmax group has pulled S(g,t) into registers: its TMEM buffer can take S(g,t+1) while exp / P are computed
-            mbar_wait(&bars[S_FREE + g], t & 1, 35 + g);
-            tc_fence_after();
-            issue_s(g, t + 1);
-          }
-          mbar_wait(&bars[P_FULL + g], t & 1, 40 + g);
-          mbar_wait(&bars[V_FULL + g], t & 1, 50 + g);
-          tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
-          const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
-          const uint32_t d = tmem_base + 256 + g * 128;
+      auto issue_pv = [&](int g, int t) {
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
+        const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
+        const uint32_t d = tmem_base + 256 + g * 128;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-            const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
-            umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
+          umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
+        }
+        umma_commit(&bars[V_EMPTY + g]);
+        umma_commit(&bars[PV_DONE + g]);
+      };
+      mbar_wait(&bars[Q_FULL], 0, 1);
+      // Event-driven issue: whichever of {S(g, next), P.V(g, next)} has its inputs ready goes to the tensor pipe next.
+      //   S(g,t)   needs K(g,t) in shared memory and the S buffer of group g drained (the group copied S(g,t-1) to registers)
+      //   P.V(g,t) needs P(g,t) written by the group and V(g,t) in shared memory
+      int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+      const int T[2] = {T0, T1};
+      uint64_t t_start = 0;
+      uint32_t idle = 0;
+      while (pv_next[0] < T0 || pv_next[1] < T1) {
+        bool progress = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          int t = s_next[g];
+          if (t < T[g] && (t == 0 || mbar_try_wait(&bars[S_FREE + g], (t - 1) & 1)) && mbar_try_wait(&bars[K_FULL + g], t & 1)) {
+            issue_s(g, t);
+            ++s_next[g];
+            progress = true;
           }
-          umma_commit(&bars[V_EMPTY + g]);
-          umma_commit(&bars[PV_DONE + g]);
+          t = pv_next[g];
+          if (t < s_next[g] && mbar_try_wait(&bars[P_FULL + g], t & 1) && mbar_try_wait(&bars[V_FULL + g], t & 1)) {
+            issue_pv(g, t);
+            ++pv_next[g];
+            progress = true;
+          }
+        }
+        if (progress) {
+          idle = 0;
+        } else if ((++idle & 0xFFF) == 0) {
+          if (t_start == 0) t_start = global_timer_ns();
+          else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
+            printf("[chronoedit_b200] attention MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],
+                   s_next[1], pv_next[0], pv_next[1]);
+            __trap();
+          }
         }
       }
     }

@@ -262,4 +262,5 @@ def test_attention_dual_source(Lq, Lk, Lk2):
         return (torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf).transpose(1, 2).reshape(B, Lq, D)
 
     ref = sdpa(kv[..., :D], kv[..., D:], Lk).bfloat16().float() + sdpa(kv2[..., :D], kv2[..., D:], Lk2).bfloat16().float()
-    _bf16_close(out, ref, f"dual attention Lq={Lq} Lk={Lk} Lk2={Lk2}", ulp=2.0, mean_tol=4e-3)
+    # a sum of two independently rounded bf16 tensors: one more rounding than a single SDPA -> 3 ulp
+    _bf16_close(out, ref, f"dual attention Lq={Lq} Lk={Lk} Lk2={Lk2}", ulp=3.0, mean_tol=5e-3)
