@@ -249,15 +249,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
       float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       mx *= sl2;
+      // lazy rescale decision (registers only): take the new max only if it grew by more than 2^8
+      float alpha = 1.0f;
+      bool need = false;
       if (t == 0) {
         m = mx;
       } else {
-        mbar_wait(&bars[PV_DONE + g], (t - 1) & 1, 70 + g);  // previous P@V of this group done: O stable, P buffer free
+        need = mx > m + RESCALE_THRESHOLD;
+        if (need) {
+          alpha = fast_exp2(m - mx);
+          m = mx;
+        }
+      }
+      // p = exp2(s*scale*log2e - m) -> packed bf16 in registers; this MUFU-bound phase overlaps the previous P.V of this group
+      const float neg_m = -m;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
+        sum4[i & 3] += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      if (t > 0) {
+        mbar_wait(&bars[PV_DONE + g], (t - 1) & 1, 70 + g);  // previous P.V of this group done: O stable, P buffer free
         tc_fence_after();
-        const bool need = mx > m + RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2(m - mx) : 1.0f;
-          if (need) m = mx;
           l *= alpha;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -271,24 +289,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           tmem_st_wait();
         }
       }
-      // p = exp2(s*scale*log2e - m) -> bf16 -> shared memory (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
-      const float neg_m = -m;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      // P -> shared memory (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[32 * c + 2 * i]), sl2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[32 * c + 2 * i + 1]), sl2, neg_m));
-          sum4[i & 3] += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
         uint8_t* row_base = p_smem + (c >> 1) * HALF_BYTES + r * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
-          *reinterpret_cast<uint4*>(row_base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          *reinterpret_cast<uint4*>(row_base + chunk * 16) =
+              make_uint4(pk[16 * c + 4 * i], pk[16 * c + 4 * i + 1], pk[16 * c + 4 * i + 2], pk[16 * c + 4 * i + 3]);
         }
       }
       l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);

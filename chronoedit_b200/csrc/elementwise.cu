@@ -8,7 +8,7 @@ namespace ce {
 namespace {
 
 constexpr int ROW_THREADS = 256;
-constexpr int MAX_D = 8192;                // 32 lanes x 32 vectors x 8 bf16
+constexpr int MAX_D = 8192;                // 64 lanes x 16 vectors x 8 bf16
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -19,32 +19,43 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One WARP per token row (8 rows per CTA): every lane keeps VPL 16-byte vectors of the row in registers, so all of a
-// row's loads are in flight at once and the statistics need warp shuffles only (no shared memory, no __syncthreads).
-template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS)
+// One WARP PAIR per token row (4 rows per 256-thread CTA): each lane keeps HV 16-byte vectors of the row in registers,
+// all of them loaded before anything consumes them; statistics = warp shuffles + one 64-thread named barrier.
+// ~100 registers/thread -> 16+ resident warps per SM, so one row's arithmetic overlaps other rows' loads.
+__device__ __forceinline__ float2 pair_sum(float a, float b, float2* part) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) part[warp] = make_float2(a, b);
+  named_bar_sync(1 + (warp >> 1), 64);
+  const float2 o = part[warp ^ 1];
+  return make_float2(a + o.x, b + o.y);
+}
+
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
                  const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
                  const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float2 part[ROW_THREADS / 32];
+  const int lane64 = threadIdx.x & 63;
+  int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;  // keep the pair barrier balanced; results are not stored
   const int nvec = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
-  uint4 v[VPL];
-  // all of the row's loads are issued before anything consumes them
+  uint4 v[HV];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + i * 32;
+  for (int i = 0; i < HV; ++i) {
+    const int idx = lane64 + i * 64;
     v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
   }
-  // single statistics pass on pivot-shifted data d = x - x[row, 0] (no cancellation even when |mean| >> std):
-  //   mean = pivot + E[d],  var = E[d^2] - E[d]^2
+  // single statistics pass on pivot-shifted data d = x - x[row, 0]:  mean = pivot + E[d],  var = E[d^2] - E[d]^2
   const float pivot = __bfloat162float(x[(size_t)row * ldx]);
   float s = 0.f, ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    if (lane + i * 32 < nvec) {
+  for (int i = 0; i < HV; ++i) {
+    if (lane64 + i * 64 < nvec) {
       float f[8];
       unpack8(v[i], f);
 #pragma unroll
@@ -55,25 +66,24 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
       }
     }
   }
-  s = warp_sum(s);
-  ss = warp_sum(ss);
-  const float md = s / (float)D;
+  const float2 tot = pair_sum(s, ss, part);
+  const float md = tot.x / (float)D;
   const float mean = pivot + md;
-  const float rstd = rsqrtf(fmaxf(ss / (float)D - md * md, 0.f) + eps);
+  const float rstd = rsqrtf(fmaxf(tot.y / (float)D - md * md, 0.f) + eps);
   const float nmr = -mean * rstd;
   const int b = row / rows_per_batch;
   uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
-  const float* pa = scale ? scale + (size_t)b * mod_stride : weight;  // multiplier table: (1 + scale) or scale, or the affine weight
+  const float* pa = scale ? scale + (size_t)b * mod_stride : weight;  // multiplier: (1 + scale) / scale / affine weight
   const float* pb = scale ? shift + (size_t)b * mod_stride : bias;
-  constexpr int G = 4;  // vectors per batch: their 4 x 4 parameter loads are in flight together
+  constexpr int G = 2;  // vectors per batch: their parameter loads are in flight together
 #pragma unroll
-  for (int i0 = 0; i0 < VPL; i0 += G) {
+  for (int i0 = 0; i0 < HV; i0 += G) {
     float4 ta[G][2], tb[G][2];
     if (pa) {
 #pragma unroll
       for (int k = 0; k < G; ++k) {
-        const int idx = lane + (i0 + k) * 32;
-        if (i0 + k < VPL && idx < nvec) {
+        const int idx = lane64 + (i0 + k) * 64;
+        if (i0 + k < HV && idx < nvec) {
           const float4* qa = reinterpret_cast<const float4*>(pa + idx * 8);
           const float4* qb = reinterpret_cast<const float4*>(pb + idx * 8);
           ta[k][0] = qa[0]; ta[k][1] = qa[1];
@@ -83,8 +93,8 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
     }
 #pragma unroll
     for (int k = 0; k < G; ++k) {
-      const int idx = lane + (i0 + k) * 32;
-      if (i0 + k < VPL && idx < nvec) {
+      const int idx = lane64 + (i0 + k) * 64;
+      if (i0 + k < HV && idx < nvec) {
         float f[8], o[8];
         unpack8(v[i0 + k], f);
 #pragma unroll
@@ -100,43 +110,46 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
             for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], av[j], bv[j]);
           }
         }
-        yr[idx] = pack8(o);
+        if (live) yr[idx] = pack8(o);
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int VPL>
-__global__ void __launch_bounds__(ROW_THREADS)
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float2 part[ROW_THREADS / 32];
+  const int lane64 = threadIdx.x & 63;
+  int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
   const int nvec = D >> 3;
   uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
-  uint4 v[VPL];
+  uint4 v[HV];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + i * 32;
+  for (int i = 0; i < HV; ++i) {
+    const int idx = lane64 + i * 64;
     v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
   }
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
+  for (int i = 0; i < HV; ++i) {
     float f[8];
     unpack8(v[i], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
   }
-  const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+  const float2 tot = pair_sum(ss, 0.f, part);
+  const float rstd = rsqrtf(tot.x / (float)D + eps);
   const int tok = rope_cos ? row % L : 0;
   const int half = head_dim >> 1;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + i * 32;
+  for (int i = 0; i < HV; ++i) {
+    const int idx = lane64 + i * 64;
     if (idx < nvec) {
       float f[8], w[8], o[8];
       unpack8(v[i], f);
@@ -158,7 +171,7 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, c
           o[2 * p + 1] = re * sv[p] + im * cv[p];
         }
       }
-      xr[idx] = pack8(o);
+      if (live) xr[idx] = pack8(o);
     }
   }
 }
@@ -283,13 +296,13 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, 
   CE_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale and shift come together");
   CE_REQUIRE((weight == nullptr) == (bias == nullptr), "layernorm: weight and bias come together");
   if (rows_per_batch <= 0) rows_per_batch = rows;
-  const int grid = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const int grid = (rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64);
   const int nvec = D / 8;
 #define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p)
-  if (nvec <= 128) CE_LN(4);
-  else if (nvec <= 256) CE_LN(8);
-  else if (nvec <= 640) CE_LN(20);
-  else CE_LN(32);
+  if (nvec <= 128) CE_LN(2);
+  else if (nvec <= 256) CE_LN(4);
+  else if (nvec <= 640) CE_LN(10);
+  else CE_LN(16);
 #undef CE_LN
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
@@ -300,13 +313,13 @@ int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16
   CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D, "rmsnorm: D must be a multiple of 8 and <= 8192");
   CE_REQUIRE(ldx % 8 == 0 && weight != nullptr, "rmsnorm: ldx % 8, weight");
   if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm: rope table / head_dim");
-  const int grid = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const int grid = (rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64);
   const int nvec = D / 8;
 #define CE_RMS(V) rmsnorm_rope_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim)
-  if (nvec <= 128) CE_RMS(4);
-  else if (nvec <= 256) CE_RMS(8);
-  else if (nvec <= 640) CE_RMS(20);
-  else CE_RMS(32);
+  if (nvec <= 128) CE_RMS(2);
+  else if (nvec <= 256) CE_RMS(4);
+  else if (nvec <= 640) CE_RMS(10);
+  else CE_RMS(16);
 #undef CE_RMS
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
