@@ -19,6 +19,8 @@
 //
 // Replaces F.scaled_dot_product_attention at /root/reference/chronoedit_diffusers/transformer_chronoedit.py:91-99
 // (self-attention, text cross-attention and image cross-attention; the latter two are summed, :103-104).
+#include <stdlib.h>
+
 #include "attention.cuh"
 
 namespace ce {
@@ -386,8 +388,20 @@ int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld)
 
 }  // namespace
 
+int launch_attention2(const AttnArgs& a, cudaStream_t stream);  // attention2.cu
+
+static bool use_attn_v2() {
+  static const bool on = [] {
+    const char* e = getenv("CE_ATTN_V2");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
+  // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
+  if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && use_attn_v2()) return launch_attention2(a, stream);
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
   CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
