@@ -10,8 +10,8 @@
 //                 ALL key tiles (running max / sum in registers, lazy rescale of O), P written back as packed bf16 into the
 //                 first 64 columns of the group's own S region (tcgen05.st) — no shared-memory round trip for P.
 // TMEM (512 columns): S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,384)  O1 [384,512).
-// Per query tile the chain S -> softmax -> P.V -> next S is serial (P aliases S), and the two query tiles interleave on the
-// tensor pipe; each K/V tile is fetched ONCE per 256 queries (half the L2->SM traffic of attention.cu).
+// Per query tile the chain S -> softmax -> P.V -> next S is serial (P aliases S; the next S is queued right behind the
+// P.V that reads P, relying on in-order execution of the MMA pipe), and the two query tiles interleave on the tensor pipe; each K/V tile is fetched ONCE per 256 queries (half the L2->SM traffic of attention.cu).
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).  attention.cu remains
 // the kernel for the two-source cross-attention and for key counts that are not worth two query tiles.
@@ -135,10 +135,11 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           bool progress = false;
 #pragma unroll
           for (int qt = 0; qt < 2; ++qt) {
-            // S_qt(j): needs K_j and the S|P region of this query tile free, i.e. P.V_qt(j-1) complete
+            // S_qt(j): needs K_j; it overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA
+            // has been ISSUED: tcgen05.mma instructions of one thread execute in issue order.  Not waiting for its
+            // completion is what lets the two query tiles fall into anti-phase on the tensor pipe.
             int j = s_next[qt];
-            if (j < n_tiles && (j == 0 || mbar_try_wait(&bars[PV_DONE + qt], (j - 1) & 1)) &&
-                mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+            if (j < n_tiles && pv_next[qt] >= j && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
               tc_fence_after();
               const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
               const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
