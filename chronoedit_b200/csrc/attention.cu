@@ -227,16 +227,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const int my_tiles = g ? T1 : T0;
     const int my_len = (dual && g) ? a.Lk2 : a.Lk;
     float m = -INFINITY, l = 0.f;
+    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tc0 = 0;
+#define CE_TICK(slot)                      \
+  if (timed) {                             \
+    const long long _t = clock64();        \
+    tacc[slot] += _t - tc0;                \
+    tc0 = _t;                              \
+  }
+    if (timed) tc0 = clock64();
 
     for (int t = 0; t < my_tiles; ++t) {
       const int valid = my_len - (dual ? t : 2 * t + g) * BKV;  // >= 1; >= 128 means no masking
       mbar_wait(&bars[S_FULL + g], t & 1, 60 + g);
       tc_fence_after();
+      CE_TICK(0)
       // the whole 128-wide score row of this thread goes to registers with one wait (4 x tcgen05.ld in flight)
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
       tmem_ld_wait();
+      CE_TICK(1)
       tc_fence_before();
       mbar_arrive(&bars[S_FREE + g]);  // S buffer drained
       if (valid < BKV) {  // last key tile only (warp-uniform): masked scores -> -inf -> p = 0
@@ -263,6 +275,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           m = mx;
         }
       }
+      CE_TICK(2)
       // p = exp2(s*scale*log2e - m) -> packed bf16 in registers; this MUFU-bound phase overlaps the previous P.V of this group
       const float neg_m = -m;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -274,6 +287,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         sum4[i & 3] += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
+      CE_TICK(3)
       if (t > 0) {
         mbar_wait(&bars[PV_DONE + g], (t - 1) & 1, 70 + g);  // previous P.V of this group done: O stable, P buffer free
         tc_fence_after();
@@ -291,6 +305,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           tmem_st_wait();
         }
       }
+      CE_TICK(4)
       // P -> shared memory (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -306,6 +321,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bars[P_FULL + g]);
+      CE_TICK(5)
+    }
+    if (timed) {
+      for (int i = 0; i < 6; ++i) a.timing[i] = tacc[i];
+      a.timing[6] = my_tiles;
     }
 
     // ---- merge the two streams and write the output tile

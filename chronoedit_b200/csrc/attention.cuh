@@ -23,6 +23,7 @@ struct AttnArgs {
   bf16* out = nullptr;      // out[b, i, h*hd + d]
   int ldo = 0;
   float scale = 0.f;        // 1/sqrt(head_dim)
+  long long* timing = nullptr;  // optional [16] device counters: phase cycles of softmax warp 4 lane 0 of block (0,0,0) (profiling aid)
   int accumulate = 0;       // 1: out = bf16(float(bf16(attn)) + float(out))   (image + text cross-attention sum)
 };
 

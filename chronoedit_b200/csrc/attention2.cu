@@ -195,15 +195,27 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
+    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tc0 = 0;
+#define CE_TICK(slot)                      \
+  if (timed) {                             \
+    const long long _t = clock64();        \
+    tacc[slot] += _t - tc0;                \
+    tc0 = _t;                              \
+  }
+    if (timed) tc0 = clock64();
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = a.Lk - j * BKV;
       mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
+      CE_TICK(0)
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
       tmem_ld_wait();
+      CE_TICK(1)
       if (valid < BKV) {
 #pragma unroll
         for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
@@ -226,6 +238,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           m = mx;
         }
       }
+      CE_TICK(2)
       const float neg_m = -m;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
@@ -236,6 +249,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         sum4[i & 3] += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
+      CE_TICK(3)
       // P.V(j-1) of this query tile completed before S(j) was even issued, so O is stable here
       if (__any_sync(0xffffffffu, need)) {
         l *= alpha;
@@ -256,6 +270,11 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt]);
+      CE_TICK(4)
+    }
+    if (timed) {
+      for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
+      a.timing[5] = n_tiles;
     }
 
     // ---- normalise and store this query tile

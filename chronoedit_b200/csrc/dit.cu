@@ -573,6 +573,14 @@ int ce_linear_bf16(const void* A, int lda, const void* W, int ldw, const void* b
   return launch_gemm_bf16(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(W), ldw, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static long long* g_attn_timing = nullptr;
+// Profiling aid: subsequent ce_attention_bf16 calls record the phase cycles of one softmax warp (block 0) into `buf`
+// ([16] int64 on the device); pass NULL to stop.
+int ce_debug_attention_timing(long long* buf) {
+  g_attn_timing = buf;
+  return CE_OK;
+}
+
 int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B, int H, int Lq,
                       int Lk, float scale, int accumulate, void* stream) {
   int rc = check_device();
@@ -585,6 +593,7 @@ int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void
   a.out = reinterpret_cast<bf16*>(out); a.ldo = ldo;
   a.scale = scale;
   a.accumulate = accumulate;
+  a.timing = g_attn_timing;
   return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

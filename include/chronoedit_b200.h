@@ -162,6 +162,10 @@ int ce_linear_bf16(const void* A, int lda, const void* W, int ldw, const void* b
 int ce_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                       int H, int Lq, int Lk, float scale, int accumulate, void* stream);
 
+/* Profiling aid: subsequent ce_attention_bf16 calls record per-phase cycle counts of one softmax warp of block 0 into `buf`
+ * (device, 16 x int64); NULL stops. */
+int ce_debug_attention_timing(long long* buf);
+
 /* Cross-attention with TWO key/value sources in one launch: out = bf16(SDPA(q,k,v)) + bf16(SDPA(q,k2,v2)) — the text and
  * image streams of ChronoEditAttnProcessor2_0 (transformer_chronoedit.py:84-104). */
 int ce_attention_dual_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* k2, int ldk2,

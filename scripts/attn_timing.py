@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Phase timing of one softmax warp (block 0) for the attention kernels: python scripts/attn_timing.py"""
+import math, os, sys, torch
+sys.path.insert(0, ".")
+import chronoedit_b200._lib as L
+lib = L.lib()
+B, H, Lq = 1, 40, 7200
+D = H * 128
+x = torch.randn(B, Lq, 3 * D, device="cuda", dtype=torch.bfloat16)
+out = torch.empty(B, Lq, D, device="cuda", dtype=torch.bfloat16)
+buf = torch.zeros(16, dtype=torch.int64, device="cuda")
+L.check(lib.ce_debug_attention_timing(L.ptr(buf)))
+for _ in range(3):
+    L.check(lib.ce_attention_bf16(L.ptr(x), 3 * D, L.ptr(x[..., D:]), 3 * D, L.ptr(x[..., 2 * D:]), 3 * D, L.ptr(out), D, B, H, Lq, Lq, 1 / math.sqrt(128), 0,
+                                  L.current_stream()))
+torch.cuda.synchronize()
+t = buf.cpu().tolist()
+v2 = os.environ.get("CE_ATTN_V2", "1") != "0"
+names = ["wait S", "ld S", "max", "exp+pack", "rescale / store P + arrive"] if v2 else ["wait S", "ld S", "max+decide", "exp+pack", "wait PV(t-1)/rescale", "store P + arrive"]
+n = t[5] if v2 else t[6]
+print("kernel:", "attention2 (v2)" if v2 else "attention (v1)", "tiles of this group:", n)
+for nm, c in zip(names, t):
+    print(f"  {nm:28s} {c / max(n,1):9.1f} cycles/tile")
+print(f"  {'total':28s} {sum(t[:len(names)]) / max(n,1):9.1f} cycles/tile")
