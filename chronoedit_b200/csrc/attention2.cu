@@ -135,28 +135,32 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           bool progress = false;
 #pragma unroll
           for (int qt = 0; qt < 2; ++qt) {
-            // S_qt(j): needs K_j; it overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA
-            // has been ISSUED: tcgen05.mma instructions of one thread execute in issue order.  Not waiting for its
-            // completion is what lets the two query tiles fall into anti-phase on the tensor pipe.
-            int j = s_next[qt];
-            if (j < n_tiles && pv_next[qt] >= j && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
-              tc_fence_after();
-              const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
-              const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
-              const uint32_t d = tmem_base + qt * 128;
+            // S_qt(j) needs K_j.  It overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA has
+            // been ISSUED (tcgen05.mma instructions of one thread execute in issue order).  Issue order matters: P.V_qt(j) is
+            // followed IMMEDIATELY by S_qt(j+1), so that the two query tiles get their next S a full 1024 cycles apart and
+            // their softmax (MUFU) phases fall into anti-phase instead of running in lockstep.
+            auto try_s = [&]() {
+              const int j = s_next[qt];
+              if (j < n_tiles && pv_next[qt] >= j && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
+                const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
+                const uint32_t d = tmem_base + qt * 128;
 #pragma unroll
-              for (int kk = 0; kk < HD / 16; ++kk) {
-                const uint32_t off = (kk >> 2) * HALF_BYTES;
-                umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3),
-                             IDESC_S, kk != 0);
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                  const uint32_t off = (kk >> 2) * HALF_BYTES;
+                  umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3),
+                               IDESC_S, kk != 0);
+                }
+                umma_commit(&bars[S_FULL + qt]);
+                ++s_next[qt];
+                if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
+                progress = true;
               }
-              umma_commit(&bars[S_FULL + qt]);
-              ++s_next[qt];
-              if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
-              progress = true;
-            }
+            };
+            try_s();
             // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
-            j = pv_next[qt];
+            const int j = pv_next[qt];
             if (j < s_next[qt] && mbar_try_wait(&bars[P_FULL + qt], j & 1) && mbar_try_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
               tc_fence_after();
               const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
@@ -169,6 +173,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
               ++pv_next[qt];
               if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
               progress = true;
+              try_s();  // S_qt(j+1) right behind P.V_qt(j)
             }
           }
           if (progress) {
