@@ -1,0 +1,342 @@
+// Self-attention forward, third generation: attention2.cu's structure (two 128-query tiles per CTA sharing every K/V tile,
+// P in TMEM, TS MMA) with 64-key tiles and TWO S|P buffers per query tile.
+//
+// With a single S|P buffer the chain S -> softmax -> P.V -> S of one query tile is serial, so each softmax group idles while
+// "its" MMAs run (measured: 1.9k of 3.7k cycles per key tile).  Here S_q(j+1) is computed into the other buffer while the
+// group is still working on S_q(j): the group runs softmax back to back and the tensor pipe always has queued work.
+//   TMEM: S|P q0b0 [0,64) q0b1 [64,128) q1b0 [128,192) q1b1 [192,256)   O0 [256,384)   O1 [384,512)
+//   smem: Q 2 x 32 KB | K ring 6 x 16 KB | V ring 4 x 16 KB
+// O may still be receiving P.V(j-1) when the group looks at S(j), so the (rare) lazy rescale first waits for that MMA.
+#include "attention.cuh"
+
+namespace ce {
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;
+constexpr int BKV = 64;
+constexpr int NK = 6;  // K ring depth
+constexpr int NV = 4;  // V ring depth
+constexpr int ATTN3_THREADS = 384;
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;   // Q tile
+constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
+constexpr uint32_t KV_BYTES = BKV * 128 * 2;       // K / V tile (64 keys)
+constexpr uint32_t KV_HALF = KV_BYTES / 2;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+
+struct Smem3 {
+  static constexpr uint32_t q = 0;                         // 2 tiles
+  static constexpr uint32_t k = q + 2 * TILE_BYTES;        // NK tiles
+  static constexpr uint32_t v = k + NK * KV_BYTES;         // NV tiles
+  static constexpr uint32_t bars = v + NV * KV_BYTES;
+  static constexpr uint32_t total = bars + 256;
+};
+
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV,  // S_FULL[q*2+buf]
+       P_FULL = S_FULL + 4, PV_DONE = P_FULL + 4, NUM_BARS3 = PV_DONE + 2 };
+
+__global__ void __launch_bounds__(ATTN3_THREADS, 1)
+attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                      const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem3::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (a.Lk + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[chronoedit_b200] attention3: dynamic shared memory not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < NUM_BARS3; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 4) ? 128 : 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (event-driven)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[Q_FULL], 2 * TILE_BYTES);
+#pragma unroll
+        for (int qt = 0; qt < 2; ++qt) {
+          tma_load_3d(smem + Smem3::q + qt * TILE_BYTES, &tma_q, &bars[Q_FULL], h * HD, q0 + qt * BQ, b);
+          tma_load_3d(smem + Smem3::q + qt * TILE_BYTES + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0 + qt * BQ, b);
+        }
+        int k_next = 0, v_next = 0;
+        uint64_t t_start = 0;
+        uint32_t idle = 0;
+        while (k_next < n_tiles || v_next < n_tiles) {
+          bool progress = false;
+          if (k_next < n_tiles) {
+            const int st = k_next % NK;
+            if (mbar_try_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
+              uint8_t* ks = smem + Smem3::k + st * KV_BYTES;
+              mbar_arrive_expect_tx(&bars[K_FULL + st], KV_BYTES);
+              tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, k_next * BKV, b);
+              tma_load_3d(ks + KV_HALF, &tma_k, &bars[K_FULL + st], h * HD + 64, k_next * BKV, b);
+              ++k_next;
+              progress = true;
+            }
+          }
+          if (v_next < n_tiles) {
+            const int st = v_next % NV;
+            if (mbar_try_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
+              uint8_t* vs = smem + Smem3::v + st * KV_BYTES;
+              mbar_arrive_expect_tx(&bars[V_FULL + st], KV_BYTES);
+              tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, v_next * BKV, b);
+              tma_load_3d(vs + KV_HALF, &tma_v, &bars[V_FULL + st], h * HD + 64, v_next * BKV, b);
+              ++v_next;
+              progress = true;
+            }
+          }
+          if (progress) {
+            idle = 0;
+          } else if ((++idle & 0xFFF) == 0) {
+            if (t_start == 0) t_start = global_timer_ns();
+            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
+              printf("[chronoedit_b200] attention3 producer stalled: block=(%d,%d,%d) k=%d v=%d\n", blockIdx.x, blockIdx.y, blockIdx.z, k_next, v_next);
+              __trap();
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (event-driven)
+      if (lane == 0) {
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, BKV, 0);   // Q (K-major, smem) x K^T (K-major, smem): N = 64 keys
+        constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
+        mbar_wait(&bars[Q_FULL], 0, 1);
+        int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+        uint64_t t_start = 0;
+        uint32_t idle = 0;
+        while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
+          bool progress = false;
+#pragma unroll
+          for (int qt = 0; qt < 2; ++qt) {
+            // S_qt(j) needs K_j.  It overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA has
+            // been ISSUED (tcgen05.mma instructions of one thread execute in issue order).  Issue order matters: P.V_qt(j) is
+            // followed IMMEDIATELY by S_qt(j+1), so that the two query tiles get their next S a full 1024 cycles apart and
+            // their softmax (MUFU) phases fall into anti-phase instead of running in lockstep.
+            auto try_s = [&]() {
+              const int j = s_next[qt];
+              // buffer j&1 of this query tile is free once P.V_qt(j-2), which reads P from it, has been issued (in-order pipe)
+              if (j < n_tiles && pv_next[qt] >= j - 1 && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(smem + Smem3::q + qt * TILE_BYTES);
+                const uint32_t k_addr = smem_u32(smem + Smem3::k + (j % NK) * KV_BYTES);
+                const uint32_t d = tmem_base + qt * 128 + (j & 1) * 64;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                  umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3),
+                               umma_desc_kmajor_sw128(k_addr + (kk >> 2) * KV_HALF) + 2 * (kk & 3), IDESC_S, kk != 0);
+                }
+                umma_commit(&bars[S_FULL + qt * 2 + (j & 1)]);
+                ++s_next[qt];
+                if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
+                progress = true;
+              }
+            };
+            try_s();
+            // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
+            const int j = pv_next[qt];
+            if (j < s_next[qt] && mbar_try_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1) &&
+                mbar_try_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
+              tc_fence_after();
+              const uint32_t v_addr = smem_u32(smem + Smem3::v + (j % NV) * KV_BYTES);
+              const uint32_t p_tmem = tmem_base + qt * 128 + (j & 1) * 64;  // packed bf16: 8 columns per K=16 step
+              const uint32_t d = tmem_base + 256 + qt * 128;
+#pragma unroll
+              for (int kk = 0; kk < BKV / 16; ++kk)
+                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, KV_HALF), IDESC_PV, (j | kk) != 0);
+              umma_commit(&bars[PV_DONE + qt]);
+              ++pv_next[qt];
+              if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
+              progress = true;
+              try_s();  // S_qt(j+1) right behind P.V_qt(j)
+            }
+          }
+          if (progress) {
+            idle = 0;
+          } else if ((++idle & 0xFFF) == 0) {
+            if (t_start == 0) t_start = global_timer_ns();
+            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
+              printf("[chronoedit_b200] attention3 MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],
+                     s_next[1], pv_next[0], pv_next[1]);
+              __trap();
+            }
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ---------------------------------------------------------------- softmax groups (one per query tile)
+    const int qt = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base + qt * 128;
+    const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
+    const float sl2 = a.scale * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tc0 = 0;
+#define CE_TICK(slot)                      \
+  if (timed) {                             \
+    const long long _t = clock64();        \
+    tacc[slot] += _t - tc0;                \
+    tc0 = _t;                              \
+  }
+    if (timed) tc0 = clock64();
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int valid = a.Lk - j * BKV;
+      const uint32_t sj_tmem = s_tmem + (j & 1) * 64;
+      mbar_wait(&bars[S_FULL + qt * 2 + (j & 1)], (j >> 1) & 1, 60 + qt);
+      tc_fence_after();
+      CE_TICK(0)
+      uint32_t s[64];
+      tmem_ld_32x32(sj_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32(sj_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
+      CE_TICK(1)
+      if (valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
+      }
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < 64; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
+      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      mx *= sl2;
+      float alpha = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m = mx;
+      } else {
+        need = mx > m + RESCALE_THRESHOLD;
+        if (need) {
+          alpha = fast_exp2(m - mx);
+          m = mx;
+        }
+      }
+      CE_TICK(2)
+      const float neg_m = -m;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
+        sum4[i & 3] += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      CE_TICK(3)
+      if (__any_sync(0xffffffffu, need)) {
+        // O still receives P.V(j-1): wait for it before touching O (rare path: the max grew by more than 2^8)
+        mbar_wait(&bars[PV_DONE + qt], (j - 1) & 1, 70 + qt);
+        tc_fence_after();
+        l *= alpha;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32(o_tmem + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(o_tmem + c * 32, o);
+        }
+      }
+      // P (packed bf16, 32 columns) overwrites the first half of this S buffer
+      tmem_st_32x32(sj_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      tmem_st_wait();
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      tc_fence_before();
+      mbar_arrive(&bars[P_FULL + qt * 2 + (j & 1)]);
+      CE_TICK(4)
+    }
+    if (timed) {
+      for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
+      a.timing[5] = n_tiles;
+    }
+
+    // ---- normalise and store this query tile
+    // phases must be consumed in order: the group may be two P.V completions behind here
+    if (n_tiles >= 2) mbar_wait(&bars[PV_DONE + qt], (n_tiles - 2) & 1, 79 + qt);
+    mbar_wait(&bars[PV_DONE + qt], (n_tiles - 1) & 1, 80 + qt);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int row = q0 + qt * BQ + r;
+    bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(o_tmem + c * 32, o);
+      tmem_ld_wait();
+      if (row < a.Lq) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[v4 * 8 + i]) * inv;
+          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) =
+              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int make_qkv_tmap3(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld, uint32_t box_rows) {
+  uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
+  uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+}  // namespace
+
+int launch_attention3(const AttnArgs& a, cudaStream_t stream) {
+  CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && a.Lk2 == 0 && a.accumulate == 0, "attention3: single source, no accumulate");
+  CE_REQUIRE(a.head_dim == HD, "attention3: only head_dim 128 is built");
+  CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention3: leading dims % 8");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_qkv_tmap3(&tq, a.q, a.B, a.Lq, a.H, a.ldq, 128))) return rc;
+  if ((rc = make_qkv_tmap3(&tk, a.k, a.B, a.Lk, a.H, a.ldk, BKV))) return rc;
+  if ((rc = make_qkv_tmap3(&tv, a.v, a.B, a.Lk, a.H, a.ldv, BKV))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem3::total));
+    attr_set = true;
+  }
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
+  attention3_fwd_kernel<<<grid, ATTN3_THREADS, Smem3::total, stream>>>(tq, tk, tv, a);
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+}  // namespace ce
