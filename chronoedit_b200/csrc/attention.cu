@@ -109,7 +109,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           const CUtensorMap* mk = (dual && g) ? &tma_k2 : &tma_k;
           const CUtensorMap* mv = (dual && g) ? &tma_v2 : &tma_v;
           int t = k_next[g];
-          if (t < T[g] && mbar_try_wait(&bars[K_EMPTY + g], (t & 1) ^ 1)) {
+          if (t < T[g] && mbar_test_wait(&bars[K_EMPTY + g], (t & 1) ^ 1)) {
             const int row0 = (dual ? t : 2 * t + g) * BKV;
             uint8_t* ks = smem + SmemLayout::k + g * TILE_BYTES;
             mbar_arrive_expect_tx(&bars[K_FULL + g], TILE_BYTES);
@@ -119,7 +119,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             progress = true;
           }
           t = v_next[g];
-          if (t < T[g] && mbar_try_wait(&bars[V_EMPTY + g], (t & 1) ^ 1)) {
+          if (t < T[g] && mbar_test_wait(&bars[V_EMPTY + g], (t & 1) ^ 1)) {
             const int row0 = (dual ? t : 2 * t + g) * BKV;
             uint8_t* vs = smem + SmemLayout::v + g * TILE_BYTES;
             mbar_arrive_expect_tx(&bars[V_FULL + g], TILE_BYTES);
@@ -188,13 +188,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           int t = s_next[g];
-          if (t < T[g] && (t == 0 || mbar_try_wait(&bars[S_FREE + g], (t - 1) & 1)) && mbar_try_wait(&bars[K_FULL + g], t & 1)) {
+          if (t < T[g] && (t == 0 || mbar_test_wait(&bars[S_FREE + g], (t - 1) & 1)) && mbar_test_wait(&bars[K_FULL + g], t & 1)) {
             issue_s(g, t);
             ++s_next[g];
             progress = true;
           }
           t = pv_next[g];
-          if (t < s_next[g] && mbar_try_wait(&bars[P_FULL + g], t & 1) && mbar_try_wait(&bars[V_FULL + g], t & 1)) {
+          if (t < s_next[g] && mbar_test_wait(&bars[P_FULL + g], t & 1) && mbar_test_wait(&bars[V_FULL + g], t & 1)) {
             issue_pv(g, t);
             ++pv_next[g];
             progress = true;

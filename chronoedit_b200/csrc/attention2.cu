@@ -91,7 +91,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           bool progress = false;
           if (k_next < n_tiles) {
             const int st = k_next % NK;
-            if (mbar_try_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
+            if (mbar_test_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
               uint8_t* ks = smem + Smem2::k + st * TILE_BYTES;
               mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
               tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, k_next * BKV, b);
@@ -102,7 +102,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
           if (v_next < n_tiles) {
             const int st = v_next % NV;
-            if (mbar_try_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
+            if (mbar_test_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
               uint8_t* vs = smem + Smem2::v + st * TILE_BYTES;
               mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
               tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, v_next * BKV, b);
@@ -141,7 +141,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             // their softmax (MUFU) phases fall into anti-phase instead of running in lockstep.
             auto try_s = [&]() {
               const int j = s_next[qt];
-              if (j < n_tiles && pv_next[qt] >= j && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+              if (j < n_tiles && pv_next[qt] >= j && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
                 const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
@@ -161,7 +161,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             try_s();
             // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
             const int j = pv_next[qt];
-            if (j < s_next[qt] && mbar_try_wait(&bars[P_FULL + qt], j & 1) && mbar_try_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
+            if (j < s_next[qt] && mbar_test_wait(&bars[P_FULL + qt], j & 1) && mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
               tc_fence_after();
               const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
               const uint32_t p_tmem = tmem_base + qt * 128;          // packed bf16: 8 columns per K=16 step

@@ -85,7 +85,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           bool progress = false;
           if (k_next < n_tiles) {
             const int st = k_next % NK;
-            if (mbar_try_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
+            if (mbar_test_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
               uint8_t* ks = smem + Smem3::k + st * KV_BYTES;
               mbar_arrive_expect_tx(&bars[K_FULL + st], KV_BYTES);
               tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, k_next * BKV, b);
@@ -96,7 +96,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
           if (v_next < n_tiles) {
             const int st = v_next % NV;
-            if (mbar_try_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
+            if (mbar_test_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
               uint8_t* vs = smem + Smem3::v + st * KV_BYTES;
               mbar_arrive_expect_tx(&bars[V_FULL + st], KV_BYTES);
               tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, v_next * BKV, b);
@@ -136,7 +136,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             auto try_s = [&]() {
               const int j = s_next[qt];
               // buffer j&1 of this query tile is free once P.V_qt(j-2), which reads P from it, has been issued (in-order pipe)
-              if (j < n_tiles && pv_next[qt] >= j - 1 && mbar_try_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+              if (j < n_tiles && pv_next[qt] >= j - 1 && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(smem + Smem3::q + qt * TILE_BYTES);
                 const uint32_t k_addr = smem_u32(smem + Smem3::k + (j % NK) * KV_BYTES);
@@ -155,8 +155,8 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             try_s();
             // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
             const int j = pv_next[qt];
-            if (j < s_next[qt] && mbar_try_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1) &&
-                mbar_try_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
+            if (j < s_next[qt] && mbar_test_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1) &&
+                mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
               tc_fence_after();
               const uint32_t v_addr = smem_u32(smem + Smem3::v + (j % NV) * KV_BYTES);
               const uint32_t p_tmem = tmem_base + qt * 128 + (j & 1) * 64;  // packed bf16: 8 columns per K=16 step

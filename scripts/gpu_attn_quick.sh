@@ -2,6 +2,4 @@
 TAG=${1:-aq}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_ops.py -k attention tests/test_gpu_dit.py -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -4 | tee gpurun_out/tests_${TAG}.log
-python scripts/attn_timing.py 2>&1 | tee gpurun_out/attn_timing_${TAG}.log
-timeout 300 python scripts/bench_ops.py attn 2>&1 | tee gpurun_out/ops_${TAG}.log
-echo "== v2"; CE_ATTN_V2=2 timeout 300 python scripts/bench_ops.py attn 2>&1 | head -1 | tee -a gpurun_out/ops_${TAG}.log
+for v in 3 2 0; do echo "== CE_ATTN_V2=$v" | tee -a gpurun_out/ops_${TAG}.log; CE_ATTN_V2=$v python scripts/attn_timing.py 2>&1 | tee -a gpurun_out/ops_${TAG}.log; CE_ATTN_V2=$v timeout 300 python scripts/bench_ops.py attn 2>&1 | tee -a gpurun_out/ops_${TAG}.log; done
