@@ -278,14 +278,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       CE_TICK(2)
       // p = exp2(s*scale*log2e - m) -> packed bf16 in registers; this MUFU-bound phase overlaps the previous P.V of this group
       const float neg_m = -m;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums (2 MUFU + 3 other instructions per pair)
+      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
-        sum4[i & 3] += p0 + p1;
+        float x0, x1;
+        f2_unpack(f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2), x0, x1);
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
+      }
+      float sum4[4];
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
+        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
+        sum4[0] = a0; sum4[1] = a1; sum4[2] = b0; sum4[3] = b1;
       }
       CE_TICK(3)
       if (t > 0) {
@@ -411,11 +421,11 @@ int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld)
 int launch_attention2(const AttnArgs& a, cudaStream_t stream);  // attention2.cu
 int launch_attention3(const AttnArgs& a, cudaStream_t stream);  // attention3.cu
 
-// CE_ATTN_V2 = 0: this file's kernel for everything; 2: attention2.cu for long single-source problems; default 3: attention3.cu
+// CE_ATTN_V2 = 0: this file's kernel for everything; 2: attention2.cu for long single-source problems; 3: attention3.cu (experimental); default 2
 static int attn_version() {
   static const int v = [] {
     const char* e = getenv("CE_ATTN_V2");
-    if (!e) return 3;
+    if (!e) return 2;
     return e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 3);
   }();
   return v;

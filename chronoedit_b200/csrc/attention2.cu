@@ -245,14 +245,24 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
       CE_TICK(2)
       const float neg_m = -m;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums (2 MUFU + 3 other instructions per pair)
+      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
-        sum4[i & 3] += p0 + p1;
+        float x0, x1;
+        f2_unpack(f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2), x0, x1);
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
+      }
+      float sum4[4];
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
+        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
+        sum4[0] = a0; sum4[1] = a1; sum4[2] = b0; sum4[3] = b1;
       }
       CE_TICK(3)
       // P.V(j-1) of this query tile completed before S(j) was even issued, so O is stable here

@@ -15,7 +15,7 @@ for _ in range(3):
                                   L.current_stream()))
 torch.cuda.synchronize()
 t = buf.cpu().tolist()
-v2 = os.environ.get("CE_ATTN_V2", "3") != "0"
+v2 = os.environ.get("CE_ATTN_V2", "2") != "0"
 names = ["wait S", "ld S", "max", "exp+pack", "rescale / store P + arrive"] if v2 else ["wait S", "ld S", "max+decide", "exp+pack", "wait PV(t-1)/rescale", "store P + arrive"]
 n = t[5] if v2 else t[6]
 print("kernel:", "attention2 (v2)" if v2 else "attention (v1)", "tiles of this group:", n)
