@@ -1,12 +1,12 @@
-// Self-attention forward, third generation: attention2.cu's structure (two 128-query tiles per CTA sharing every K/V tile,
-// P in TMEM, TS MMA) with 64-key tiles and TWO S|P buffers per query tile.
-//
-// With a single S|P buffer the chain S -> softmax -> P.V -> S of one query tile is serial, so each softmax group idles while
-// "its" MMAs run (measured: 1.9k of 3.7k cycles per key tile).  Here S_q(j+1) is computed into the other buffer while the
-// group is still working on S_q(j): the group runs softmax back to back and the tensor pipe always has queued work.
-//   TMEM: S|P q0b0 [0,64) q0b1 [64,128) q1b0 [128,192) q1b1 [192,256)   O0 [256,384)   O1 [384,512)
-//   smem: Q 2 x 32 KB | K ring 6 x 16 KB | V ring 4 x 16 KB
-// O may still be receiving P.V(j-1) when the group looks at S(j), so the (rare) lazy rescale first waits for that MMA.
+// Self-attention forward, third generation.  Two 128-query tiles per CTA share every K/V tile (as attention2.cu), but
+//   * key tiles are 64 wide, so one query tile needs only 64 TMEM columns for S and P gets its OWN columns
+//     (two 32-column buffers): S(j+1) no longer has to wait for P.V(j) -- it is issued the moment the softmax group has
+//     pulled S(j) into registers, and is ready long before the group finishes exp / P(j);
+//   * each query tile has its own MMA issuer thread (warp 1 / warp 2): the events of one chain strictly alternate
+//     (S drained -> issue next S;  P written -> issue P.V), so plain blocking waits in program order suffice.
+// The softmax groups therefore run back to back (MUFU-bound: 2 x 64 x 128 exp2 per 64-key step = the MMA time of that step).
+//   TMEM:  q0: S [0,64) P [64,96) [96,128)   q1: S [128,192) P [192,224) [224,256)   O0 [256,384)   O1 [384,512)
+//   smem:  Q 2 x 32 KB | K ring 6 x 16 KB | V ring 4 x 16 KB
 #include "attention.cuh"
 
 namespace ce {
@@ -33,8 +33,8 @@ struct Smem3 {
   static constexpr uint32_t total = bars + 256;
 };
 
-enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV,  // S_FULL[q*2+buf]
-       P_FULL = S_FULL + 4, PV_DONE = P_FULL + 4, NUM_BARS3 = PV_DONE + 2 };
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV, S_FREE = S_FULL + 2,
+       P_FULL = S_FREE + 2 /* [q*2 + buf] */, PV_DONE = P_FULL + 4, NUM_BARS3 = PV_DONE + 2 };
 
 __global__ void __launch_bounds__(ATTN3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -55,7 +55,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       printf("[chronoedit_b200] attention3: dynamic shared memory not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < NUM_BARS3; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 4) ? 128 : 1);
+    for (int i = 0; i < NUM_BARS3; ++i) mbar_init(&bars[i], (i >= S_FREE && i < P_FULL + 4) ? 128 : ((i >= K_EMPTY && i < K_EMPTY + NK) || (i >= V_EMPTY && i < V_EMPTY + NV) ? 2 : 1));
     fence_mbar_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -116,71 +116,43 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
         }
       }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer (event-driven)
+    } else if (warp == 1 || warp == 2) {
+      // ---------------------------------------------------------------- MMA issuers: warp 1 -> query tile 0, warp 2 -> query tile 1
       if (lane == 0) {
         constexpr uint32_t IDESC_S = umma_idesc_bf16(128, BKV, 0);   // Q (K-major, smem) x K^T (K-major, smem): N = 64 keys
-        constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
+        constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem): K = 64 keys
+        const int qt = warp - 1;
+        const uint32_t q_addr = smem_u32(smem + Smem3::q + qt * TILE_BYTES);
+        const uint32_t s_tm = tmem_base + qt * 128;
+        const uint32_t o_tm = tmem_base + 256 + qt * 128;
+        auto issue_s = [&](int j) {
+          mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30 + qt);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(smem + Smem3::k + (j % NK) * KV_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_bf16_ss(s_tm, umma_desc_kmajor_sw128(q_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3),
+                         umma_desc_kmajor_sw128(k_addr + (kk >> 2) * KV_HALF) + 2 * (kk & 3), IDESC_S, kk != 0);
+          umma_commit(&bars[S_FULL + qt]);
+          umma_commit(&bars[K_EMPTY + j % NK]);  // one of the two arrivals (both query tiles consume K_j)
+        };
         mbar_wait(&bars[Q_FULL], 0, 1);
-        int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
-        uint64_t t_start = 0;
-        uint32_t idle = 0;
-        while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
-          bool progress = false;
-#pragma unroll
-          for (int qt = 0; qt < 2; ++qt) {
-            // S_qt(j) needs K_j.  It overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA has
-            // been ISSUED (tcgen05.mma instructions of one thread execute in issue order).  Issue order matters: P.V_qt(j) is
-            // followed IMMEDIATELY by S_qt(j+1), so that the two query tiles get their next S a full 1024 cycles apart and
-            // their softmax (MUFU) phases fall into anti-phase instead of running in lockstep.
-            auto try_s = [&]() {
-              const int j = s_next[qt];
-              // buffer j&1 of this query tile is free once P.V_qt(j-2), which reads P from it, has been issued (in-order pipe)
-              if (j < n_tiles && pv_next[qt] >= j - 1 && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
-                tc_fence_after();
-                const uint32_t q_addr = smem_u32(smem + Smem3::q + qt * TILE_BYTES);
-                const uint32_t k_addr = smem_u32(smem + Smem3::k + (j % NK) * KV_BYTES);
-                const uint32_t d = tmem_base + qt * 128 + (j & 1) * 64;
-#pragma unroll
-                for (int kk = 0; kk < HD / 16; ++kk) {
-                  umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3),
-                               umma_desc_kmajor_sw128(k_addr + (kk >> 2) * KV_HALF) + 2 * (kk & 3), IDESC_S, kk != 0);
-                }
-                umma_commit(&bars[S_FULL + qt * 2 + (j & 1)]);
-                ++s_next[qt];
-                if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
-                progress = true;
-              }
-            };
-            try_s();
-            // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
-            const int j = pv_next[qt];
-            if (j < s_next[qt] && mbar_test_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1) &&
-                mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
-              tc_fence_after();
-              const uint32_t v_addr = smem_u32(smem + Smem3::v + (j % NV) * KV_BYTES);
-              const uint32_t p_tmem = tmem_base + qt * 128 + (j & 1) * 64;  // packed bf16: 8 columns per K=16 step
-              const uint32_t d = tmem_base + 256 + qt * 128;
-#pragma unroll
-              for (int kk = 0; kk < BKV / 16; ++kk)
-                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, KV_HALF), IDESC_PV, (j | kk) != 0);
-              umma_commit(&bars[PV_DONE + qt]);
-              ++pv_next[qt];
-              if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
-              progress = true;
-              try_s();  // S_qt(j+1) right behind P.V_qt(j)
-            }
+        issue_s(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) {
+            mbar_wait(&bars[S_FREE + qt], j & 1, 35 + qt);  // the group holds S(j) in registers: overwrite the S columns
+            issue_s(j + 1);
           }
-          if (progress) {
-            idle = 0;
-          } else if ((++idle & 0xFFF) == 0) {
-            if (t_start == 0) t_start = global_timer_ns();
-            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
-              printf("[chronoedit_b200] attention3 MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],
-                     s_next[1], pv_next[0], pv_next[1]);
-              __trap();
-            }
-          }
+          mbar_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1, 40 + qt);
+          mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 50 + qt);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem + Smem3::v + (j % NV) * KV_BYTES);
+          const uint32_t p_tm = s_tm + 64 + (j & 1) * 32;  // packed bf16: 8 columns per K=16 step
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk)
+            umma_bf16_ts(o_tm, p_tm + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, KV_HALF), IDESC_PV, (j | kk) != 0);
+          umma_commit(&bars[PV_DONE + qt]);
+          umma_commit(&bars[V_EMPTY + j % NV]);
         }
       }
     }
@@ -195,6 +167,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
+    bool pv_waited = false;
     const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
@@ -208,14 +181,15 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = a.Lk - j * BKV;
-      const uint32_t sj_tmem = s_tmem + (j & 1) * 64;
-      mbar_wait(&bars[S_FULL + qt * 2 + (j & 1)], (j >> 1) & 1, 60 + qt);
+      mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
       CE_TICK(0)
       uint32_t s[64];
-      tmem_ld_32x32(sj_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld_32x32(sj_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[S_FREE + qt]);  // S columns may be overwritten by S(j+1)
       CE_TICK(1)
       if (valid < BKV) {
 #pragma unroll
@@ -241,7 +215,6 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
       CE_TICK(2)
       const float neg_m = -m;
-      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums (2 MUFU + 3 other instructions per pair)
       const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[32];
@@ -253,19 +226,21 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
       }
-      float sum4[4];
       {
         float a0, a1, b0, b1;
         f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
         f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
-        sum4[0] = a0; sum4[1] = a1; sum4[2] = b0; sum4[3] = b1;
+        l = fmaf(l, alpha, (a0 + a1) + (b0 + b1));  // old sum moves to the new reference (alpha = 1 unless the max jumped)
       }
       CE_TICK(3)
+      // P buffer j&1 was last read by P.V(j-2): consume the PV_DONE phases strictly in order (j-2 here, j-1 only if O must
+      // be rescaled now, otherwise at the next tile)
+      if (j >= 2 && !pv_waited) mbar_wait(&bars[PV_DONE + qt], (j - 2) & 1, 70 + qt);
+      pv_waited = false;
       if (__any_sync(0xffffffffu, need)) {
-        // O still receives P.V(j-1): wait for it before touching O (rare path: the max grew by more than 2^8)
-        mbar_wait(&bars[PV_DONE + qt], (j - 1) & 1, 70 + qt);
+        mbar_wait(&bars[PV_DONE + qt], (j - 1) & 1, 71 + qt);  // O still receives P.V(j-1)
+        pv_waited = true;                                      // phase j-1 already consumed: skip it at tile j+1
         tc_fence_after();
-        l *= alpha;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -276,10 +251,9 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tmem_st_32x32(o_tmem + c * 32, o);
         }
       }
-      // P (packed bf16, 32 columns) overwrites the first half of this S buffer
-      tmem_st_32x32(sj_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      tc_fence_after();
+      tmem_st_32x32(s_tmem + 64 + (j & 1) * 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
       tmem_st_wait();
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt * 2 + (j & 1)]);
       CE_TICK(4)
@@ -290,8 +264,8 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     }
 
     // ---- normalise and store this query tile
-    // phases must be consumed in order: the group may be two P.V completions behind here
-    if (n_tiles >= 2) mbar_wait(&bars[PV_DONE + qt], (n_tiles - 2) & 1, 79 + qt);
+    // the remaining PV_DONE phases, in order (n-2 unless already consumed by a rescale at the last tile, then n-1)
+    if (n_tiles >= 2 && !pv_waited) mbar_wait(&bars[PV_DONE + qt], (n_tiles - 2) & 1, 79 + qt);
     mbar_wait(&bars[PV_DONE + qt], (n_tiles - 1) & 1, 80 + qt);
     tc_fence_after();
     const float inv = 1.0f / l;
