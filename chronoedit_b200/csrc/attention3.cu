@@ -30,11 +30,11 @@ struct Smem3 {
   static constexpr uint32_t k = q + 2 * TILE_BYTES;        // NK tiles
   static constexpr uint32_t v = k + NK * KV_BYTES;         // NV tiles
   static constexpr uint32_t bars = v + NV * KV_BYTES;
-  static constexpr uint32_t total = bars + 256;
+  static constexpr uint32_t total = bars + 512;
 };
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV, S_FREE = S_FULL + 2,
-       P_FULL = S_FREE + 2 /* [q*2 + buf] */, PV_DONE = P_FULL + 4, NUM_BARS3 = PV_DONE + 2 };
+       P_FULL = S_FREE + 2 /* [q*2 + buf] */, PV_DONE = P_FULL + 4 /* [q*2 + buf] */, NUM_BARS3 = PV_DONE + 4 };
 
 __global__ void __launch_bounds__(ATTN3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -151,7 +151,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk)
             umma_bf16_ts(o_tm, p_tm + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, KV_HALF), IDESC_PV, (j | kk) != 0);
-          umma_commit(&bars[PV_DONE + qt]);
+          umma_commit(&bars[PV_DONE + qt * 2 + (j & 1)]);
           umma_commit(&bars[V_EMPTY + j % NV]);
         }
       }
@@ -167,7 +167,6 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    bool pv_waited = false;
     const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
@@ -233,13 +232,11 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         l = fmaf(l, alpha, (a0 + a1) + (b0 + b1));  // old sum moves to the new reference (alpha = 1 unless the max jumped)
       }
       CE_TICK(3)
-      // P buffer j&1 was last read by P.V(j-2): consume the PV_DONE phases strictly in order (j-2 here, j-1 only if O must
-      // be rescaled now, otherwise at the next tile)
-      if (j >= 2 && !pv_waited) mbar_wait(&bars[PV_DONE + qt], (j - 2) & 1, 70 + qt);
-      pv_waited = false;
+      // P buffer j&1 was last read by P.V(j-2).  One PV_DONE barrier per buffer, so a wait never lags its barrier by
+      // more than one phase (P.V(j) cannot be issued before this thread publishes P(j)).
+      if (j >= 2) mbar_wait(&bars[PV_DONE + qt * 2 + (j & 1)], ((j - 2) >> 1) & 1, 70 + qt);
       if (__any_sync(0xffffffffu, need)) {
-        mbar_wait(&bars[PV_DONE + qt], (j - 1) & 1, 71 + qt);  // O still receives P.V(j-1)
-        pv_waited = true;                                      // phase j-1 already consumed: skip it at tile j+1
+        mbar_wait(&bars[PV_DONE + qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 72 + qt);  // O still receives P.V(j-1)
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -264,9 +261,8 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     }
 
     // ---- normalise and store this query tile
-    // the remaining PV_DONE phases, in order (n-2 unless already consumed by a rescale at the last tile, then n-1)
-    if (n_tiles >= 2 && !pv_waited) mbar_wait(&bars[PV_DONE + qt], (n_tiles - 2) & 1, 79 + qt);
-    mbar_wait(&bars[PV_DONE + qt], (n_tiles - 1) & 1, 80 + qt);
+    // the last P.V (commits complete in issue order, so every earlier one is done too)
+    mbar_wait(&bars[PV_DONE + qt * 2 + ((n_tiles - 1) & 1)], ((n_tiles - 1) >> 1) & 1, 80 + qt);
     tc_fence_after();
     const float inv = 1.0f / l;
     const int row = q0 + qt * BQ + r;
