@@ -34,7 +34,7 @@ struct Smem3 {
 };
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV, S_FREE = S_FULL + 2,
-       P_FULL = S_FREE + 2 /* [q*2 + buf] */, PV_DONE = P_FULL + 4 /* [q*2 + buf] */, NUM_BARS3 = PV_DONE + 4 };
+       P_FULL = S_FREE + 2 /* [q*2 + buf] */, PV_DONE = P_FULL + 4 /* [q*2 + buf] */, STAGGER = PV_DONE + 4, NUM_BARS3 = STAGGER + 1 };
 
 __global__ void __launch_bounds__(ATTN3_THREADS, 1)
 attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -55,7 +55,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       printf("[chronoedit_b200] attention3: dynamic shared memory not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < NUM_BARS3; ++i) mbar_init(&bars[i], (i >= S_FREE && i < P_FULL + 4) ? 128 : ((i >= K_EMPTY && i < K_EMPTY + NK) || (i >= V_EMPTY && i < V_EMPTY + NV) ? 2 : 1));
+    for (int i = 0; i < NUM_BARS3; ++i) mbar_init(&bars[i], ((i >= S_FREE && i < P_FULL + 4) || i == STAGGER) ? 128 : ((i >= K_EMPTY && i < K_EMPTY + NK) || (i >= V_EMPTY && i < V_EMPTY + NV) ? 2 : 1));
     fence_mbar_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -68,7 +68,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (event-driven)
       if (lane == 0) {
@@ -137,6 +137,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           umma_commit(&bars[K_EMPTY + j % NK]);  // one of the two arrivals (both query tiles consume K_j)
         };
         mbar_wait(&bars[Q_FULL], 0, 1);
+        if (qt == 1) mbar_wait(&bars[STAGGER], 0, 2);  // start behind query tile 0 so the two exp phases interleave
         issue_s(0);
         for (int j = 0; j < n_tiles; ++j) {
           if (j + 1 < n_tiles) {
@@ -157,7 +158,7 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ---------------------------------------------------------------- softmax groups (one per query tile)
     const int qt = (warp - 4) >> 2;
     const int quad = warp & 3;
@@ -166,7 +167,8 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t s_tmem = tmem_base + lane_base + qt * 128;
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
+    float m, l = 0.f, alpha = 1.0f;
+    bool need = false;
     const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
@@ -176,54 +178,58 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     tacc[slot] += _t - tc0;                \
     tc0 = _t;                              \
   }
-    if (timed) tc0 = clock64();
 
-    for (int j = 0; j < n_tiles; ++j) {
-      const int valid = a.Lk - j * BKV;
-      mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
-      tc_fence_after();
-      CE_TICK(0)
-      uint32_t s[64];
-      tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&bars[S_FREE + qt]);  // S columns may be overwritten by S(j+1)
-      CE_TICK(1)
+    // Software pipeline: while tile j is exponentiated (MUFU-bound), S(j+1) is pulled into the other register array and
+    // its row maximum is folded in between the exp2 instructions.  `cur` holds S(j) with m / alpha / need already decided.
+    auto mask_tail = [&](uint32_t (&t)[64], int valid) {
       if (valid < BKV) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
+        for (int i = 0; i < 64; ++i) t[i] = (i < valid) ? t[i] : 0xff800000u;
       }
-      float mx8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
-#pragma unroll
-      for (int i = 8; i < 64; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
-      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      mx *= sl2;
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m = mx;
-      } else {
-        need = mx > m + RESCALE_THRESHOLD;
-        if (need) {
-          alpha = fast_exp2(m - mx);
-          m = mx;
-        }
+    };
+    auto exp_pair = [&](const uint32_t (&cur)[64], uint32_t (&pk)[32], uint64_t (&sum2)[4], int i, uint64_t sl2_2, uint64_t negm_2) {
+      float x0, x1;
+      f2_unpack(f2_fma(f2_pack_bits(cur[2 * i], cur[2 * i + 1]), sl2_2, negm_2), x0, x1);
+      const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+      sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
+      pk[i] = pack_bf16x2(p0, p1);
+    };
+    auto step = [&](uint32_t (&cur)[64], uint32_t (&nxt)[64], int j) {
+      const bool has_next = j + 1 < n_tiles;
+      if (has_next) {
+        mbar_wait(&bars[S_FULL + qt], (j + 1) & 1, 60 + qt);
+        tc_fence_after();
+        tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&nxt[0]));
+        tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&nxt[32]));
       }
-      CE_TICK(2)
+      CE_TICK(0)
       const float neg_m = -m;
       const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x0, x1;
-        f2_unpack(f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2), x0, x1);
-        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
-        pk[i] = pack_bf16x2(p0, p1);
+      for (int i = 0; i < 16; ++i) exp_pair(cur, pk, sum2, i, sl2_2, negm_2);
+      CE_TICK(1)
+      float mx8[8];
+      if (has_next) {
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[S_FREE + qt]);  // S columns may be overwritten by S(j+2)
+        mask_tail(nxt, a.Lk - (j + 1) * BKV);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(nxt[i]);
+      }
+      CE_TICK(2)
+#pragma unroll
+      for (int i = 16; i < 32; ++i) {
+        exp_pair(cur, pk, sum2, i, sl2_2, negm_2);
+        if (has_next && i >= 18) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 8 + (i - 18) * 4 + e;
+            mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(nxt[c]));
+          }
+        }
       }
       {
         float a0, a1, b0, b1;
@@ -250,10 +256,45 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
       tc_fence_after();
       tmem_st_32x32(s_tmem + 64 + (j & 1) * 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      // decide the reference for tile j+1 while the store is in flight
+      alpha = 1.0f;
+      need = false;
+      if (has_next) {
+        const float mx = sl2 * fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        need = mx > m + RESCALE_THRESHOLD;
+        if (need) {
+          alpha = fast_exp2(m - mx);
+          m = mx;
+        }
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt * 2 + (j & 1)]);
       CE_TICK(4)
+    };
+
+    uint32_t sA[64], sB[64];
+    mbar_wait(&bars[S_FULL + qt], 0, 60 + qt);
+    tc_fence_after();
+    tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sA[0]));
+    tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sA[32]));
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&bars[S_FREE + qt]);
+    if (qt == 0) mbar_arrive(&bars[STAGGER]);  // query tile 1 starts half a period behind (the two groups share the MUFU)
+    mask_tail(sA, a.Lk);
+    {
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sA[i]);
+#pragma unroll
+      for (int i = 8; i < 64; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sA[i]));
+      m = sl2 * fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+    }
+    if (timed) tc0 = clock64();
+    for (int j = 0; j < n_tiles; j += 2) {
+      step(sA, sB, j);
+      if (j + 1 < n_tiles) step(sB, sA, j + 1);
     }
     if (timed) {
       for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
