@@ -139,10 +139,15 @@ attention3_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         mbar_wait(&bars[Q_FULL], 0, 1);
         if (qt == 1) mbar_wait(&bars[STAGGER], 0, 2);  // start behind query tile 0 so the two exp phases interleave
         issue_s(0);
+        if (n_tiles > 1) {
+          mbar_wait(&bars[S_FREE + qt], 0, 35 + qt);  // S(0) is in the group's registers
+          issue_s(1);
+        }
         for (int j = 0; j < n_tiles; ++j) {
-          if (j + 1 < n_tiles) {
-            mbar_wait(&bars[S_FREE + qt], j & 1, 35 + qt);  // the group holds S(j) in registers: overwrite the S columns
-            issue_s(j + 1);
+          if (j + 2 < n_tiles) {
+            // the group pulls S(j+1) into registers in the middle of its tile-j step: S(j+2) is then ready when that step ends
+            mbar_wait(&bars[S_FREE + qt], (j + 1) & 1, 35 + qt);
+            issue_s(j + 2);
           }
           mbar_wait(&bars[P_FULL + qt * 2 + (j & 1)], (j >> 1) & 1, 40 + qt);
           mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 50 + qt);
