@@ -15,6 +15,8 @@
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).  attention.cu remains
 // the kernel for the two-source cross-attention and for key counts that are not worth two query tiles.
+#include <cstdlib>
+
 #include "attention.cuh"
 
 namespace ce {
@@ -40,8 +42,10 @@ struct Smem2 {
 };
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV,
-       P_FULL = S_FULL + 2, PV_DONE = P_FULL + 2, NUM_BARS2 = PV_DONE + 2 };
+       P_FULL = S_FULL + 2 /* [half*2 + q]: keys 0-63 / 64-127 of the tile */, PV_DONE = P_FULL + 4, NUM_BARS2 = PV_DONE + 2 };
 
+// POLY of every 4 exp2 pairs are evaluated on the FMA pipe (f2_exp2_poly), the rest on the MUFU
+template <int POLY>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
@@ -61,7 +65,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       printf("[chronoedit_b200] attention2: dynamic shared memory not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < NUM_BARS2; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 2) ? 128 : 1);
+    for (int i = 0; i < NUM_BARS2; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 4) ? 128 : 1);
     fence_mbar_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -128,7 +132,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major, smem) x K^T (K-major, smem)
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
         mbar_wait(&bars[Q_FULL], 0, 1);
-        int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+        int s_next[2] = {0, 0}, pv_next[2] = {0, 0}, pv_half[2] = {0, 0};
         uint64_t t_start = 0;
         uint32_t idle = 0;
         while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
@@ -159,21 +163,33 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
               }
             };
             try_s();
-            // P.V_qt(j): needs P_qt(j) in TMEM and V_j in shared memory
+            // P.V_qt(j) in two K halves: keys 0-63 as soon as the group has published the first half of P (it is still
+            // exponentiating the second half), keys 64-127 when the rest is there.  Needs V_j in shared memory.
             const int j = pv_next[qt];
-            if (j < s_next[qt] && mbar_test_wait(&bars[P_FULL + qt], j & 1) && mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
-              tc_fence_after();
+            if (j < s_next[qt]) {
               const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
               const uint32_t p_tmem = tmem_base + qt * 128;          // packed bf16: 8 columns per K=16 step
               const uint32_t d = tmem_base + 256 + qt * 128;
+              if (pv_half[qt] == 0 && mbar_test_wait(&bars[P_FULL + qt], j & 1) && mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
+                tc_fence_after();
 #pragma unroll
-              for (int kk = 0; kk < BKV / 16; ++kk)
-                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
-              umma_commit(&bars[PV_DONE + qt]);
-              ++pv_next[qt];
-              if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
-              progress = true;
-              try_s();  // S_qt(j+1) right behind P.V_qt(j)
+                for (int kk = 0; kk < BKV / 32; ++kk)
+                  umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
+                pv_half[qt] = 1;
+                progress = true;
+              }
+              if (pv_half[qt] == 1 && mbar_test_wait(&bars[P_FULL + 2 + qt], j & 1)) {
+                tc_fence_after();
+#pragma unroll
+                for (int kk = BKV / 32; kk < BKV / 16; ++kk)
+                  umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, 1);
+                umma_commit(&bars[PV_DONE + qt]);
+                pv_half[qt] = 0;
+                ++pv_next[qt];
+                if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
+                progress = true;
+                try_s();  // S_qt(j+1) right behind P.V_qt(j)
+              }
             }
           }
           if (progress) {
@@ -244,27 +260,6 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         }
       }
       CE_TICK(2)
-      const float neg_m = -m;
-      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums (2 MUFU + 3 other instructions per pair)
-      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
-      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float x0, x1;
-        f2_unpack(f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2), x0, x1);
-        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
-        pk[i] = pack_bf16x2(p0, p1);
-      }
-      float sum4[4];
-      {
-        float a0, a1, b0, b1;
-        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
-        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
-        sum4[0] = a0; sum4[1] = a1; sum4[2] = b0; sum4[3] = b1;
-      }
-      CE_TICK(3)
       // P.V(j-1) of this query tile completed before S(j) was even issued, so O is stable here
       if (__any_sync(0xffffffffu, need)) {
         l *= alpha;
@@ -278,13 +273,49 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tmem_st_32x32(o_tmem + c * 32, o);
         }
       }
-      // P (packed bf16, 64 columns) overwrites the first half of this group's S region
+      const float neg_m = -m;
+      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums; 2 MUFU (or the FMA-pipe polynomial) per pair
+      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pk[64];
+      auto exp_pair = [&](int i) {
+        const uint64_t x2 = f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2);
+        float p0, p1;
+        if ((i & 3) < POLY) {
+          f2_exp2_poly(x2, p0, p1);
+        } else {
+          float x0, x1;
+          f2_unpack(x2, x0, x1);
+          p0 = fast_exp2(x0);
+          p1 = fast_exp2(x1);
+        }
+        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+      };
+      // P (packed bf16, 64 columns) overwrites the first half of this group's S region, published in two halves so that
+      // the tensor pipe starts on P.V while the second half is still being exponentiated
+#pragma unroll
+      for (int i = 0; i < 32; ++i) exp_pair(i);
+      tc_fence_after();
       tmem_st_32x32(s_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-      tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+#pragma unroll
+      for (int i = 32; i < 40; ++i) exp_pair(i);
       tmem_st_wait();
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt]);
+      CE_TICK(3)
+#pragma unroll
+      for (int i = 40; i < 64; ++i) exp_pair(i);
+      tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
+        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[P_FULL + 2 + qt]);
       CE_TICK(4)
     }
     if (timed) {
@@ -339,13 +370,27 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap2(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap2(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap2(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
+  // developer knob: CE_ATTN_POLY = how many of every 4 exp2 pairs run on the FMA pipe (0..3)
+  static const int poly = [] {
+    const char* e = getenv("CE_ATTN_POLY");
+    const int v = e ? atoi(e) : 1;
+    return v < 0 ? 0 : (v > 3 ? 3 : v);
+  }();
   static bool attr_set = false;
   if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
+    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
     attr_set = true;
   }
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-  attention2_fwd_kernel<<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);
+  switch (poly) {
+    case 0: attention2_fwd_kernel<0><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
+    case 1: attention2_fwd_kernel<1><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
+    case 2: attention2_fwd_kernel<2><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
+    default: attention2_fwd_kernel<3><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
+  }
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }
