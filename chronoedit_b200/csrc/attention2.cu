@@ -373,7 +373,7 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   // developer knob: CE_ATTN_POLY = how many of every 4 exp2 pairs run on the FMA pipe (0..3)
   static const int poly = [] {
     const char* e = getenv("CE_ATTN_POLY");
-    const int v = e ? atoi(e) : 1;
+    const int v = e ? atoi(e) : 0;
     return v < 0 ? 0 : (v > 3 ? 3 : v);
   }();
   static bool attr_set = false;

@@ -52,6 +52,23 @@ def bench_attn(B=2, H=40, Lq=7200, Lk=7200, nbuf=3):
     print(json.dumps({"op": "attention", "B": B, "H": H, "Lq": Lq, "Lk": Lk, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
 
 
+def bench_attn_dual(B=2, H=40, Lq=7200, Lk=512, Lk2=257):
+    """The cross-attention launch of the DiT block: text keys + image keys in one kernel."""
+    D = H * 128
+    q = torch.randn(B, Lq, D, device="cuda", dtype=torch.bfloat16)
+    kv = torch.randn(B, Lk, 2 * D, device="cuda", dtype=torch.bfloat16)
+    kv2 = torch.randn(B, Lk2, 2 * D, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, Lq, D, device="cuda", dtype=torch.bfloat16)
+
+    def fn():
+        L.check(lib.ce_attention_dual_bf16(L.ptr(q), D, L.ptr(kv), 2 * D, L.ptr(kv[..., D:]), 2 * D, L.ptr(kv2), 2 * D, L.ptr(kv2[..., D:]), 2 * D,
+                                           L.ptr(out), D, B, H, Lq, Lk, Lk2, 1 / math.sqrt(128), L.current_stream()))
+
+    ms = timeit(fn)
+    fl = 4.0 * B * H * Lq * (Lk + Lk2) * 128
+    print(json.dumps({"op": "attention_dual", "B": B, "H": H, "Lq": Lq, "Lk": Lk, "Lk2": Lk2, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+
+
 def bench_gemm(M, N, K, epi=0, nbuf=3):
     A = [torch.randn(M, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
     W = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(nbuf)]
@@ -114,6 +131,7 @@ if __name__ == "__main__":
         bench_attn(B=1)
         bench_attn(Lk=512)
         bench_attn(Lk=257)
+        bench_attn_dual()
     if "gemm" in what:
         for (M, N, K, epi) in [(14400, 15360, 5120, 0), (14400, 5120, 5120, 3), (14400, 13824, 5120, 1), (14400, 5120, 13824, 3), (7200, 5120, 5120, 0)]:
             bench_gemm(M, N, K, epi)
