@@ -419,14 +419,13 @@ int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld)
 }  // namespace
 
 int launch_attention2(const AttnArgs& a, cudaStream_t stream);  // attention2.cu
-int launch_attention3(const AttnArgs& a, cudaStream_t stream);  // attention3.cu
 
-// CE_ATTN_V2 = 0: this file's kernel for everything; 2: attention2.cu for long single-source problems; 3: attention3.cu (experimental); default 2
+// developer knob CE_ATTN_V2=0: this file's kernel for everything (A/B against attention2.cu); default: attention2.cu for long
+// single-source problems
 static int attn_version() {
   static const int v = [] {
     const char* e = getenv("CE_ATTN_V2");
-    if (!e) return 2;
-    return e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 3);
+    return (e && e[0] == '0') ? 0 : 2;
   }();
   return v;
 }
@@ -435,7 +434,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
   // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
   if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && attn_version() != 0)
-    return attn_version() == 2 ? launch_attention2(a, stream) : launch_attention3(a, stream);
+    return launch_attention2(a, stream);
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
   CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");
