@@ -1,7 +1,7 @@
 // Micro-benchmark: back-to-back tcgen05.mma issue rate per SM for the shapes the attention kernels use.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o mma_rate mma_rate.cu -lcuda && ./mma_rate
 // mode 0: SS  M128 N64  K16 (Q.K^T with 64-key tiles)      mode 1: SS M128 N128 K16      mode 2: SS M128 N256 K16
-// mode 3: TS  M128 N128 K16 (P in TMEM, V MN-major)        mode 4: alternate mode-0 and mode-3 groups (attention3 mix)
+// mode 3: TS  M128 N128 K16 (P in TMEM, V MN-major)        mode 4: alternate mode-0 and mode-3 groups (64-key-tile mix)
 // mode 5: alternate mode-1 and mode-3 groups (attention2 mix)
 #include <cstdio>
 #include <cuda_runtime.h>
