@@ -32,11 +32,24 @@ class DiTConfigC(ctypes.Structure):
     ]
 
 
+class UniPCStepArgsC(ctypes.Structure):   # ce_unipc_step_args (field order = include/chronoedit_b200.h)
+    _fields_ = [
+        ("sample_dtype", c_int32), ("model_dtype", c_int32), ("n", c_int64), ("cond", c_void_p), ("uncond", c_void_p),
+        ("guidance", c_float), ("sigma", c_float), ("sample", c_void_p), ("last_sample", c_void_p), ("m_prev", c_void_p),
+        ("m_prev2", c_void_p), ("use_corrector", c_int32), ("c_order", c_int32), ("c_x", c_float), ("c_m0", c_float),
+        ("c_bh", c_float), ("c_inv_rk", c_float), ("c_rho0", c_float), ("c_rho1", c_float), ("p_order", c_int32),
+        ("p_x", c_float), ("p_m0", c_float), ("p_bh", c_float), ("p_inv_rk", c_float), ("p_zero", c_float),
+        ("x0_out", c_void_p), ("corrected_out", c_void_p), ("prev_sample_out", c_void_p), ("model_input_out", c_void_p),
+        ("inner", c_int64), ("c_lat", c_int32), ("c_total", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/chronoedit_b200.h declares
 SIGNATURES = {
     "ce_abi_version": (c_int, []),
     "ce_last_error": (c_char_p, []),
     "ce_device_check": (c_int, []),
+    "ce_unipc_step": (c_int, [POINTER(UniPCStepArgsC), c_void_p]),
     "ce_dit_create": (c_int, [POINTER(DiTConfigC), POINTER(c_void_p)]),
     "ce_dit_destroy": (None, [c_void_p]),
     "ce_dit_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int64]),

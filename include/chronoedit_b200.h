@@ -186,6 +186,50 @@ int ce_rmsnorm_rope_bf16(void* x, int ldx, int rows, int D, float eps, const voi
 int ce_rope_table_host(int head_dim, int frames, int height_patches, int width_patches, int max_seq_len,
                        int temporal_skip_len, float theta, float* cos_out_host, float* sin_out_host);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Sampling glue either side of the DiT call: one launch per denoising step for
+ *   noise = uncond + g*(cond - uncond)                                   chronoedit_diffusers/pipeline_chronoedit.py:736
+ *   FlowUniPCMultistepScheduler.step: x0 conversion, UniC corrector, UniP predictor (solver_order 2, bh2, predict_x0,
+ *   flow_prediction, lower_order_final)                                  chronoedit/_src/models/fm_solvers_unipc.py:670-756
+ *   channels [0, c_lat) of the next cat([latents, condition], 1).to(bf16) pipeline_chronoedit.py:712
+ * Every intermediate is rounded to the tensor dtype exactly where the reference's separate torch kernels round, so the
+ * result is bit-identical to running the reference on CUDA.  The scalar coefficients are the caller's business (the Python
+ * mirror chronoedit_b200/scheduler.py computes them with the same fp32 CPU tensor ops as the reference, :418-447, :565-620);
+ * divisions by r_k arrive as the fp32 reciprocal because that is how torch's CUDA `tensor / scalar` evaluates.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define CE_DTYPE_F32 0
+#define CE_DTYPE_BF16 1
+
+typedef struct ce_unipc_step_args {
+  int32_t sample_dtype;          /* dtype of sample / last_sample / m_prev* / outputs: CE_DTYPE_F32 | CE_DTYPE_BF16 */
+  int32_t model_dtype;           /* dtype of cond / uncond; (f32,f32) (f32,bf16) (bf16,bf16) are built */
+  int64_t n;                     /* elements of the latent [B, c_lat, T, H, W] */
+  const void* cond;              /* model output (conditional) */
+  const void* uncond;            /* model output (unconditional) or NULL: no guidance */
+  float guidance;
+  float sigma;                   /* sigmas[step_index]: x0 = sample - sigma * v                       (:340-341) */
+  const void* sample;            /* x_t */
+  const void* last_sample;       /* sample before the previous predictor; corrector only                (:567) */
+  const void* m_prev;            /* model_outputs[-1] before this call (x0 prediction of the previous step) or NULL */
+  const void* m_prev2;           /* model_outputs[-2] before this call or NULL */
+  int32_t use_corrector;         /* step_index > 0 and last_sample is set                               (:701-705) */
+  int32_t c_order;               /* 1 | 2: this_order of the previous step */
+  float c_x, c_m0, c_bh;         /* sigma_t/sigma_s0, alpha_t*h_phi_1, alpha_t*B_h at (step_index, step_index-1) */
+  float c_inv_rk, c_rho0, c_rho1;/* order 2: 1/r_k and solve(R, b) cast to the sample dtype; order 1 uses 0.5 */
+  int32_t p_order;               /* 1 | 2: min(2, steps - step_index, lower_order_nums + 1)             (:729-737) */
+  float p_x, p_m0, p_bh;         /* the same three scalars at (step_index+1, step_index) */
+  float p_inv_rk;                /* order 2 */
+  float p_zero;                  /* order 1: alpha_t*B_h*0, still subtracted by the reference (sign of zero) */
+  void* x0_out;                  /* -> model_outputs[-1] */
+  void* corrected_out;           /* -> last_sample (written only when use_corrector) */
+  void* prev_sample_out;         /* -> returned sample */
+  void* model_input_out;         /* optional bf16 [B, c_total, inner]: channels [0, c_lat) <- prev_sample; NULL = skip */
+  int64_t inner;                 /* T*H*W */
+  int32_t c_lat, c_total;        /* 16, 36 */
+} ce_unipc_step_args;
+
+int ce_unipc_step(const ce_unipc_step_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,3 +18,11 @@ def scale_lora_layers(model, weight):
 
 def unscale_lora_layers(model, weight=None):
     return None
+
+
+def deprecate(*args, **kwargs):  # diffusers.utils.deprecate: warns only
+    return None
+
+
+def is_scipy_available():
+    return False

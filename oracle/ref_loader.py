@@ -12,6 +12,8 @@ What is loaded, and how:
     resolve to `oracle/diffusers_shim/diffusers`.
   * VAE: `chronoedit/_src/tokenizers/wan2pt1.py` executed as-is with
     `sys.modules` stubs for its infra-only imports (wan2pt1.py:26-31).
+  * UniPC flow-matching scheduler: `chronoedit/_src/models/fm_solvers_unipc.py` executed as-is; its diffusers
+    imports (fm_solvers_unipc.py:24-28) resolve to the shim.
   * DiffSynth DiT modules (`chronoedit_diffsynth/wan_video_dit_chronoedit.py`)
     as an independent in-tree cross-check, with two import stubs.
 """
@@ -105,3 +107,14 @@ def load_reference_diffsynth_dit():
     mod.FLASH_ATTN_3_AVAILABLE = False
     mod.SAGE_ATTN_AVAILABLE = False
     return mod
+
+
+def load_reference_unipc():
+    """Returns the module object of the reference fm_solvers_unipc.py (class FlowUniPCMultistepScheduler)."""
+    if "_ref_fm_solvers_unipc" in sys.modules:
+        return sys.modules["_ref_fm_solvers_unipc"]
+    try:
+        import diffusers  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, _SHIM)
+    return _load_by_path("_ref_fm_solvers_unipc", os.path.join(REFERENCE_ROOT, "chronoedit", "_src", "models", "fm_solvers_unipc.py"))
