@@ -250,14 +250,22 @@ def run_ours(args):
     d_text = text.to(dev, torch.bfloat16)
     d_img = img.to(dev, torch.bfloat16)
 
+    # The loop body of ChronoEditPipeline.__call__ (pipeline_chronoedit.py:693-739) on device-resident tensors: model input =
+    # cat([latents, condition]) in bf16, ONE batch-2 DiT call for the CFG pair, then ONE fused launch for the guidance combine
+    # + UniPC flow-matching scheduler step + the latent channels of the next model input (chronoedit_b200/scheduler.py).
+    from chronoedit_b200.scheduler import FlowUniPCMultistepScheduler
+
+    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    d_lat = d_lat.to(torch.bfloat16)   # the diffusers pipeline keeps bf16 latents (pipeline_chronoedit.py:676-687)
+    d_in = torch.cat([d_lat, d_cond], dim=1).contiguous()
+
     def device_step(i):
         nonlocal d_lat
-        s0, s1 = float(sigmas[i % 50]), float(sigmas[i % 50 + 1])
-        t = torch.full((B,), int(s0 * 1000) % 1000, device=dev, dtype=torch.int64)
-        x = torch.cat([d_lat.to(torch.bfloat16), d_cond], dim=1).expand(2, -1, -1, -1, -1)
-        out = model(x, t, d_text, d_img, return_dict=False)[0]
-        pred = out[1:2].float() + GUIDANCE * (out[0:1].float() - out[1:2].float())
-        d_lat = d_lat + (s1 - s0) * pred
+        if sched.step_index is None or sched.step_index >= 50:
+            sched.set_timesteps(50, device=dev, shift=5.0)   # flow shift 5 (run_inference_diffusers.py:203-207)
+        t = sched.timesteps[sched.step_index or 0]
+        out = model(d_in.expand(2, -1, -1, -1, -1), t.expand(2), d_text, d_img, return_dict=False)[0]
+        d_lat = sched.step_cfg(out[0:1], out[1:2], GUIDANCE, t, d_lat, model_input_out=d_in)
 
     # host-buffer (e2e) step: pinned inputs, H2D + forward + D2H inside the C-ABI call, glue on the host
     h_x = torch.empty(2, 36, FRAMES, LAT_H, LAT_W, dtype=torch.bfloat16).pin_memory()
@@ -316,7 +324,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     dev_ms, wall_ms, prof, clocks = timed(device_step, args.steps, args.warmup, sampler, profile=True)
-    launches = model.launches_per_forward() * args.steps
+    launches = (model.launches_per_forward() + 1) * args.steps   # + the fused sampler launch
     value = world * args.steps / (dev_ms / 1000.0)
     e2e_dev_ms, e2e_wall_ms, _, _ = timed(host_step, max(3, args.steps // 2), 1)
     e2e_steps = max(3, args.steps // 2)
@@ -385,7 +393,7 @@ def run_ours(args):
                             "512 text + 257 image tokens, CFG 5.0 (2 forwards/step as one batch-2 call), per-GPU independent edits",
                 "layers": args.layers, "global_batch_edits": world, "parallelism": f"dp{world}",
                 "l2": "inputs larger than L2 (32.8 GB of weights stream every forward); no explicit flush",
-                "latent_update": "flow-matching Euler update in torch (scheduler is a 'next' row)",
+                "latent_update": "value: fused CFG + FlowUniPC step + next model input in one launch (ce_unipc_step); e2e: host-side Euler glue around ce_dit_forward_host",
                 "cross_kv_hoisting": False,
             },
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -3,6 +3,7 @@
 Public surface (drop-in for the objects `ChronoEditPipeline` registers, pipeline_chronoedit.py:175-183):
   ChronoEditTransformer3DModel   <- chronoedit_diffusers/transformer_chronoedit.py:298-476
   AutoencoderKLWan               <- diffusers AutoencoderKLWan (arithmetic twin: chronoedit/_src/tokenizers/wan2pt1.py)
+  FlowUniPCMultistepScheduler    <- chronoedit/_src/models/fm_solvers_unipc.py (the per-step glue either side of the DiT call)
 Both call hand-written CUDA kernels in lib/libchronoedit_b200.so through the C ABI of include/chronoedit_b200.h.
 Importing this package does not need a GPU; running anything does (there is no CPU fallback).
 """
@@ -13,3 +14,6 @@ __all__ = ["ChronoEditTransformer3DModel", "Transformer2DModelOutput", "CEError"
 from .autoencoder import AutoencoderKLWan  # noqa: E402,F401
 
 __all__.append("AutoencoderKLWan")
+from .scheduler import FlowUniPCMultistepScheduler  # noqa: E402,F401
+
+__all__.append("FlowUniPCMultistepScheduler")
