@@ -13,13 +13,21 @@ pipeline_chronoedit.py:676-687; fp32 in the native loop, chronoedit_14b_edit_mod
 are fp32 0-dim CPU tensors.  The restatement keeps the same op order and the same rounding points, written as one flat
 formula list per step so that the fused CUDA kernel can be checked against it op for op.
 
-`recip_div`: torch's CUDA `a / scalar` multiplies by the fp32 reciprocal (ATen BinaryDivTrueKernel.cu), its CPU kernel
-divides.  The reference runs on CUDA; the golden vectors are generated on CPU (no GPU in the build container).  The oracle
-therefore has both: `recip_div=False` is pinned bit-exactly against the unmodified reference on CPU (tests/golden/unipc_*),
-`recip_div=True` is what the CUDA kernel is compared with.
+CPU vs CUDA torch semantics.  The reference runs on CUDA; the golden vectors are generated on CPU (no GPU in the build
+container).  torch evaluates `tensor (op) 0-dim-fp32-CPU-scalar` differently on the two devices (ATen, headers in this image):
+  * CPU: TensorIterator first casts the scalar operand to the common dtype (bf16 latents -> the COEFFICIENT is rounded to
+    bf16), then the kernel runs;  CUDA: `gpu_kernel_with_scalars` reads the scalar at full fp32 precision
+    (ATen/native/cuda/Loops.cuh:185-232, `iter.scalar_value<opmath_t>`), no operand cast;
+  * `tensor / scalar`: CPU divides; CUDA multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu).
+The formulas below are written with ordinary torch ops, so they follow the device the tensors live on:
+  * on CPU tensors they reproduce the unmodified reference bit for bit (tests/golden/unipc_*, the pin);
+  * on CUDA tensors (tests/test_gpu_sampler.py) they are what the reference computes on a GPU -- the fused kernel is required
+    to match THAT bit for bit;
+  * `cuda_semantics=True` emulates the CUDA behaviour with CPU tensors (explicit fp32 scalar math, reciprocal multiply) for
+    places that have no GPU torch run to compare with (smoke()); the GPU tests check the emulation against the real thing.
 
 Pinning: tests/golden/make_golden_unipc.py runs the UNMODIFIED reference file through oracle/diffusers_shim and stores
-per-step samples; tests/test_oracle_unipc.py requires bit equality (bf16 and fp32).
+per-step samples; tests/test_sampler_cpu.py requires bit equality (bf16 and fp32).
 """
 from __future__ import annotations
 
@@ -106,42 +114,66 @@ def _t(v: float) -> torch.Tensor:   # fp32 0-dim CPU tensor: scalar operand that
     return torch.tensor(v, dtype=torch.float32)
 
 
-def _div(a, rk: float, recip_div: bool):
-    if recip_div:
-        return a * _t(float(np.float32(1.0) / np.float32(rk)))
-    return a / _t(rk)
+class _Ops:
+    """tensor-with-scalar ops either as torch evaluates them on the tensor's device (`emulate_cuda=False`) or with CUDA's
+    scalar handling spelled out on CPU tensors (`emulate_cuda=True`)."""
+
+    def __init__(self, emulate_cuda: bool):
+        self.emu = emulate_cuda
+
+    def smul(self, s: float, t: torch.Tensor) -> torch.Tensor:
+        if self.emu:
+            return (t.float() * _t(s)).to(t.dtype)
+        return _t(s) * t
+
+    def ssub(self, t: torch.Tensor, s: float) -> torch.Tensor:
+        if self.emu:
+            return (t.float() - _t(s)).to(t.dtype)
+        return t - _t(s)
+
+    def sdiv(self, t: torch.Tensor, s: float) -> torch.Tensor:
+        if self.emu:
+            return (t.float() * _t(float(np.float32(1.0) / np.float32(s)))).to(t.dtype)
+        return t / _t(s)
+
+    def pymul(self, g: float, t: torch.Tensor) -> torch.Tensor:   # Python-number operand (guidance scale)
+        if self.emu:
+            return (t.float() * _t(float(np.float32(g)))).to(t.dtype)
+        return g * t
 
 
-def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance: float) -> torch.Tensor:
-    return uncond + guidance * (cond - uncond)   # pipeline_chronoedit.py:736
+def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance: float, cuda_semantics: bool = False) -> torch.Tensor:
+    return uncond + _Ops(cuda_semantics).pymul(guidance, cond - uncond)   # pipeline_chronoedit.py:736
 
 
-def step_formulas(c: StepCoeffs, v, x, last, m_prev, m_prev2, recip_div: bool):
+def step_formulas(c: StepCoeffs, v, x, last, m_prev, m_prev2, cuda_semantics: bool = False):
     """One scheduler step as a flat formula list -> (x0 prediction, corrected sample, next sample)."""
-    m_t = x - _t(c.sigma) * v
+    o = _Ops(cuda_semantics)
+    dev = x.device
+    m_t = x - o.smul(c.sigma, v)
     if c.use_corrector:
-        xt_ = _t(c.c_x) * last - _t(c.c_m0) * m_prev
+        xt_ = o.smul(c.c_x, last) - o.smul(c.c_m0, m_prev)
         d_t = m_t - m_prev
         if c.c_order == 1:
-            inner = 0 + torch.tensor(0.5, dtype=last.dtype) * d_t
+            inner = 0 + torch.tensor(0.5, dtype=last.dtype, device=dev) * d_t
         else:
-            d1 = _div(m_prev2 - m_prev, c.c_rk, recip_div)
-            inner = torch.tensor(c.c_rho0, dtype=last.dtype) * d1 + torch.tensor(c.c_rho1, dtype=last.dtype) * d_t
-        x = (xt_ - _t(c.c_bh) * inner).to(last.dtype)
-    xt_ = _t(c.p_x) * x - _t(c.p_m0) * m_t
+            d1 = o.sdiv(m_prev2 - m_prev, c.c_rk)
+            inner = torch.tensor(c.c_rho0, dtype=last.dtype, device=dev) * d1 + torch.tensor(c.c_rho1, dtype=last.dtype, device=dev) * d_t
+        x = (xt_ - o.smul(c.c_bh, inner)).to(last.dtype)
+    xt_ = o.smul(c.p_x, x) - o.smul(c.p_m0, m_t)
     if c.p_order == 1:
-        nxt = xt_ - _t(c.p_zero)
+        nxt = o.ssub(xt_, c.p_zero)
     else:
-        d1 = _div(m_prev - m_t, c.p_rk, recip_div)
-        nxt = xt_ - _t(c.p_bh) * (torch.tensor(0.5, dtype=x.dtype) * d1)
+        d1 = o.sdiv(m_prev - m_t, c.p_rk)
+        nxt = xt_ - o.smul(c.p_bh, torch.tensor(0.5, dtype=x.dtype, device=dev) * d1)
     return m_t, x, nxt.to(x.dtype)
 
 
 class UniPCOracle:
     """Stateful wrapper with the reference object's surface: set_timesteps / step / model_outputs / last_sample."""
 
-    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0, recip_div: bool = False):
-        self.num_train_timesteps, self.base_shift, self.recip_div = num_train_timesteps, shift, recip_div
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0, cuda_semantics: bool = False):
+        self.num_train_timesteps, self.base_shift, self.cuda_semantics = num_train_timesteps, shift, cuda_semantics
         self.model_outputs: List[Optional[torch.Tensor]] = [None, None]
         self.last_sample = None
 
@@ -155,7 +187,7 @@ class UniPCOracle:
     def step(self, v: torch.Tensor, sample: torch.Tensor) -> torch.Tensor:
         i = self.step_index
         c = step_coeffs(self.sigmas, i, self.n, self.lower_order_nums, self.this_order, self.last_sample is not None, sample.dtype)
-        m_t, x, nxt = step_formulas(c, v, sample, self.last_sample, self.model_outputs[1], self.model_outputs[0], self.recip_div)
+        m_t, x, nxt = step_formulas(c, v, sample, self.last_sample, self.model_outputs[1], self.model_outputs[0], self.cuda_semantics)
         self.model_outputs = [self.model_outputs[1], m_t]
         self.this_order, self.last_sample = c.p_order, x
         self.lower_order_nums = min(self.lower_order_nums + 1, 2)

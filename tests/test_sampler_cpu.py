@@ -17,8 +17,8 @@ def _bits(t):
     return t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32)
 
 
-def _run_oracle(case, recip_div=False):
-    o = unipc_oracle.UniPCOracle(shift=1.0, recip_div=recip_div)
+def _run_oracle(case, cuda_semantics=False):
+    o = unipc_oracle.UniPCOracle(shift=1.0, cuda_semantics=cuda_semantics)
     o.set_timesteps(case.steps, shift=case.shift)
     x, cond, uncond = case_inputs(case)
     outs = []
@@ -29,7 +29,7 @@ def _run_oracle(case, recip_div=False):
         c, u = cond[i], uncond[i]
         if case.cut_at is not None and i >= case.cut_at:
             c, u = c[:, :, [0, -1]], u[:, :, [0, -1]]
-        v = unipc_oracle.cfg_combine(c, u, case.guidance) if case.guidance is not None else c
+        v = unipc_oracle.cfg_combine(c, u, case.guidance, cuda_semantics) if case.guidance is not None else c
         x = o.step(v, x)
         outs.append(x)
     return o, outs
@@ -61,17 +61,19 @@ def test_oracle_matches_live_reference():
         assert torch.equal(_bits(x), _bits(outs[i]))
 
 
-def test_reciprocal_division_is_a_last_ulp_effect(golden_dir):
-    """torch's CUDA `t / scalar` multiplies by the reciprocal; that is the only modelled CPU/CUDA difference and it stays
-    within one fp32 ulp of the divided value (and never shows after bf16 rounding in the recorded cases)."""
+def test_cuda_scalar_semantics_are_a_rounding_level_effect(golden_dir):
+    """torch's CUDA kernels keep fp32 coefficients at full precision and multiply by 1/r_k where the CPU kernels round the
+    coefficient to the tensor dtype and divide (oracle/unipc_oracle.py header).  The emulated CUDA mode must stay within a few
+    ulps of the tensor dtype from the CPU-run reference -- this is the tolerance the GPU tests use against the golden vectors."""
     man = json.load(open(os.path.join(golden_dir, "UNIPC_MANIFEST.json")))["cases"]
     for name, case in UNIPC_CASES.items():
-        _, a = _run_oracle(case, recip_div=False)
-        _, b = _run_oracle(case, recip_div=True)
+        _, a = _run_oracle(case, cuda_semantics=False)
+        _, b = _run_oracle(case, cuda_semantics=True)
         n_diff = sum(int((x != y).sum()) for x, y in zip(a, b))
-        assert n_diff == man[name]["elements_changed_by_reciprocal_division"]
+        assert n_diff == man[name]["elements_changed_by_cuda_semantics"]
+        tol = 2e-6 if case.sample_dtype == torch.float32 else 4 * 2.0 ** -8   # a few bf16 ulps, accumulated over the steps
         for x, y in zip(a, b):
-            torch.testing.assert_close(x.float(), y.float(), rtol=2e-6, atol=2e-6)
+            torch.testing.assert_close(x.float(), y.float(), rtol=tol, atol=tol)
 
 
 # ---------------------------------------------------------------------------------------------- product mirror, host side
