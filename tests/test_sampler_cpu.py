@@ -61,19 +61,23 @@ def test_oracle_matches_live_reference():
         assert torch.equal(_bits(x), _bits(outs[i]))
 
 
-def test_cuda_scalar_semantics_are_a_rounding_level_effect(golden_dir):
-    """torch's CUDA kernels keep fp32 coefficients at full precision and multiply by 1/r_k where the CPU kernels round the
-    coefficient to the tensor dtype and divide (oracle/unipc_oracle.py header).  The emulated CUDA mode must stay within a few
-    ulps of the tensor dtype from the CPU-run reference -- this is the tolerance the GPU tests use against the golden vectors."""
+def test_cuda_scalar_semantics_distance_is_as_recorded(golden_dir):
+    """torch's CUDA kernels keep fp32 coefficients at full precision and multiply by 1/r_k where its CPU kernels round the
+    coefficient to the tensor dtype first and divide (oracle/unipc_oracle.py header).  With bf16 latents that is a visible
+    difference between a CPU and a GPU run OF THE REFERENCE ITSELF (coefficients lose 8 of their 24 bits on CPU and the update
+    subtracts nearly equal terms).  The golden vectors are a CPU run; the manifest records how far the emulated CUDA semantics
+    land from them, and the GPU tests bound the kernel-vs-golden distance by that number.  With fp32 latents and fp32 model
+    outputs only the division differs and the distance is one rounding."""
     man = json.load(open(os.path.join(golden_dir, "UNIPC_MANIFEST.json")))["cases"]
     for name, case in UNIPC_CASES.items():
         _, a = _run_oracle(case, cuda_semantics=False)
         _, b = _run_oracle(case, cuda_semantics=True)
         n_diff = sum(int((x != y).sum()) for x, y in zip(a, b))
+        max_diff = max(float((x.float() - y.float()).abs().max()) for x, y in zip(a, b))
         assert n_diff == man[name]["elements_changed_by_cuda_semantics"]
-        tol = 2e-6 if case.sample_dtype == torch.float32 else 4 * 2.0 ** -8   # a few bf16 ulps, accumulated over the steps
-        for x, y in zip(a, b):
-            torch.testing.assert_close(x.float(), y.float(), rtol=tol, atol=tol)
+        assert max_diff == man[name]["max_abs_change_by_cuda_semantics"]
+        if case.sample_dtype == torch.float32 and case.model_dtype == torch.float32:
+            assert max_diff <= 2.5e-7 * max(1.0, max(float(x.abs().max()) for x in a))
 
 
 # ---------------------------------------------------------------------------------------------- product mirror, host side
