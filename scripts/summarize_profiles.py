@@ -28,7 +28,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "smsp__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_tensor.sum"]
-for k in ("gemm", "attn", "conv"):
+for k in ("gemm", "attn", "xattn", "rows", "conv"):
     rep = f"gpurun_out/prof_{k}_{tag}.ncu-rep"
     if not os.path.exists(rep): continue
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
