@@ -1,17 +1,18 @@
 // Self-attention forward, cluster generation: a cluster of TWO CTAs shares every K/V tile through TMA multicast (each CTA
 // fetches half of the tile and the copy lands in both CTAs' shared memory: same L2->SM traffic as attention2.cu), but every
 // CTA owns ONE 128-query tile and therefore the whole 512 TMEM columns of its SM:
-//     S0 [0,128)  S1 [128,256)   two score buffers: S(j+1), S(j+2) are computed while the softmax still works on tile j
+//     S0 [0,128)  S1 [128,256)   score buffers of the even / odd key tiles
 //     P0 [256,320) P1 [320,384)  P (packed bf16) has its own columns: nothing aliases, no serial S -> P -> P.V -> S chain
-//     O  [384,512)
-// The tensor pipe never waits for the softmax of the SAME tile and the softmax never waits for the tensor pipe: the kernel
-// is bound by the softmax throughput of one SM (16 ex2/clk -> 1024 clk per 128x128 tile, the same as the MMA time of a tile).
-//
-// 384 threads: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 4-11 softmax: TWO threads per query row (warps w
-// and w+4 address the same TMEM lanes; each takes 64 of the 128 score columns, 64 of the 128 output columns), partial row
-// maxima / sums exchanged through shared memory with a 64-thread named barrier per warp pair.  The softmax loop is software
-// pipelined: while tile j is exponentiated (MUFU-bound) the 64 scores of tile j+1 are pulled into a second register array
-// and their maximum is folded in between the ex2 instructions.
+//     O  [384,512)               ONE accumulator
+// 384 threads: warp 0 TMA producer, warp 1 MMA issuer (one thread, event driven), warps 4-7 softmax group A = even key tiles,
+// warps 8-11 group B = odd key tiles, one thread per query row each.  Both groups feed the SAME accumulator, so they share the
+// running row maximum: the thread that handles tile j reads m(j-1) from a per-row mailbox in shared memory (published by the
+// other group right after its max phase), decides m(j) with the usual lazy threshold, publishes it, and -- in the rare case of
+// a jump -- rescales O itself once P.V(j-1) has completed.  Only this short decide step is serial; the long phases (TMEM
+// load, row max, 128 exp2, P store) of consecutive tiles overlap, which keeps the MUFU (16 ex2/clk/SM = 1024 clk per
+// 128x128 tile, the same as the MMA time of a tile) busy.  Each thread keeps the partial row sum of its own tiles relative
+// to the maximum it used last; the two partial sums are brought to the final maximum and added at the end.
+// The result is the same sequence of operations per row as attention2.cu (same threshold decisions, same bf16 P).
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).
 #include <cstdlib>
@@ -25,7 +26,7 @@ namespace {
 constexpr int HD = 128;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int NK = 4;  // K ring depth (S is issued up to three tiles ahead of the softmax)
+constexpr int NK = 4;  // K ring depth (S is issued two tiles ahead of the softmax)
 constexpr int NV = 2;  // V ring depth
 constexpr int ATTN4_THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;
@@ -38,14 +39,14 @@ struct Smem4 {
   static constexpr uint32_t q = 0;
   static constexpr uint32_t k = q + TILE_BYTES;
   static constexpr uint32_t v = k + NK * TILE_BYTES;
-  static constexpr uint32_t xchg = v + NV * TILE_BYTES;   // 2 x 2 x 128 floats: partial row maxima (double buffered), reused for the row sums
+  static constexpr uint32_t xchg = v + NV * TILE_BYTES;   // 2 x 2 x 128 floats: [tile parity][0: running max m(j), 1: partial row sum][row]
   static constexpr uint32_t bars = xchg + 2 * 2 * 128 * 4;
   static constexpr uint32_t total = bars + 192;
 };
 static_assert(Smem4::total <= 227 * 1024, "attention4: shared memory budget");
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV, S_FREE = S_FULL + 2,
-       P_FULL = S_FREE + 2, PV_DONE = P_FULL + 2, NUM_BARS4 = PV_DONE + 2 };
+       P_FULL = S_FREE + 2, PV_DONE = P_FULL + 2, M_PUB = PV_DONE + 2, NUM_BARS4 = M_PUB + 2 };
 static_assert(NUM_BARS4 * 8 + 8 <= 192, "attention4: barrier block");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN4_THREADS, 1)
@@ -72,7 +73,7 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     for (int i = 0; i < NUM_BARS4; ++i) {
       uint32_t count = 1;
       if ((i >= K_EMPTY && i < K_EMPTY + NK) || (i >= V_EMPTY && i < V_EMPTY + NV)) count = 2;   // one commit from each CTA
-      if (i >= S_FREE && i < P_FULL + 2) count = 256;                                              // every softmax thread
+      if ((i >= S_FREE && i < P_FULL + 2) || i >= M_PUB) count = 128;                              // every thread of one softmax group
       mbar_init(&bars[i], count);
     }
     fence_mbar_init();
@@ -141,58 +142,72 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
         const uint32_t q_addr = smem_u32(smem + Smem4::q);
         const uint32_t o_tm = tmem_base + 384;
-        auto issue_s = [&](int j) {
-          mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30);
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(smem + Smem4::k + (j % NK) * TILE_BYTES);
-          const uint32_t d = tmem_base + (j & 1) * 128;
-#pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) {
-            const uint32_t off = (kk >> 2) * HALF_BYTES;
-            umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S, kk != 0);
-          }
-          umma_commit(&bars[S_FULL + (j & 1)]);
-          umma_commit_mc(&bars[K_EMPTY + j % NK], BOTH_CTAS);
-        };
         mbar_wait(&bars[Q_FULL], 0, 1);
-        issue_s(0);
-        if (n_tiles > 1) issue_s(1);
-        if (n_tiles > 2) {
-          mbar_wait(&bars[S_FREE + 0], 0, 34);  // S(0) is in the softmax registers
-          issue_s(2);
-        }
-        for (int k = 0; k < n_tiles; ++k) {
-          if (k + 3 < n_tiles) {
-            // the softmax pulls S(k+1) into registers in the middle of its tile-k step: S(k+3) takes that buffer
-            mbar_wait(&bars[S_FREE + ((k + 1) & 1)], ((k + 1) >> 1) & 1, 35);
-            issue_s(k + 3);
-          }
-          mbar_wait(&bars[P_FULL + (k & 1)], (k >> 1) & 1, 40);
-          mbar_wait(&bars[V_FULL + k % NV], (k / NV) & 1, 50);
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(smem + Smem4::v + (k % NV) * TILE_BYTES);
-          const uint32_t p_tm = tmem_base + 256 + (k & 1) * 64;  // packed bf16: 8 columns per K=16 step
+        int s_next = 0, pv_next = 0;
+        uint64_t t_start = 0;
+        uint32_t idle = 0;
+        while (pv_next < n_tiles) {
+          bool progress = false;
+          // S(j) -> buffer j&1: free once the group of that parity has pulled S(j-2) into registers (early in its step)
+          if (s_next < n_tiles) {
+            const int j = s_next;
+            if ((j < 2 || mbar_test_wait(&bars[S_FREE + (j & 1)], ((j - 2) >> 1) & 1)) && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+              tc_fence_after();
+              const uint32_t k_addr = smem_u32(smem + Smem4::k + (j % NK) * TILE_BYTES);
+              const uint32_t d = tmem_base + (j & 1) * 128;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk)
-            umma_bf16_ts(o_tm, p_tm + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (k | kk) != 0);
-          umma_commit(&bars[PV_DONE + (k & 1)]);
-          umma_commit_mc(&bars[V_EMPTY + k % NV], BOTH_CTAS);
+              for (int kk = 0; kk < HD / 16; ++kk) {
+                const uint32_t off = (kk >> 2) * HALF_BYTES;
+                umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S, kk != 0);
+              }
+              umma_commit(&bars[S_FULL + (j & 1)]);
+              umma_commit_mc(&bars[K_EMPTY + j % NK], BOTH_CTAS);
+              ++s_next;
+              progress = true;
+            }
+          }
+          // O += P(k) V(k)
+          {
+            const int k = pv_next;
+            if (k < s_next && mbar_test_wait(&bars[P_FULL + (k & 1)], (k >> 1) & 1) && mbar_test_wait(&bars[V_FULL + k % NV], (k / NV) & 1)) {
+              tc_fence_after();
+              const uint32_t v_addr = smem_u32(smem + Smem4::v + (k % NV) * TILE_BYTES);
+              const uint32_t p_tm = tmem_base + 256 + (k & 1) * 64;  // packed bf16: 8 columns per K=16 step
+#pragma unroll
+              for (int kk = 0; kk < BKV / 16; ++kk)
+                umma_bf16_ts(o_tm, p_tm + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (k | kk) != 0);
+              umma_commit(&bars[PV_DONE + (k & 1)]);
+              umma_commit_mc(&bars[V_EMPTY + k % NV], BOTH_CTAS);
+              ++pv_next;
+              progress = true;
+            }
+          }
+          if (progress) {
+            idle = 0;
+          } else if ((++idle & 0xFFF) == 0) {
+            if (t_start == 0) t_start = global_timer_ns();
+            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
+              printf("[chronoedit_b200] attention4 MMA stalled: block=(%d,%d,%d) s=%d pv=%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next, pv_next);
+              __trap();
+            }
+          }
         }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    // ---------------------------------------------------------------- softmax: two threads per query row
-    const int half = (warp - 4) >> 2;   // which 64 score columns / 64 output columns
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ---------------------------------------------------------------- softmax groups: A = even key tiles, B = odd key tiles
+    const int grp = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_base + half * 64;            // + (j&1)*128
-    const uint32_t p_tmem = tmem_base + lane_base + 256 + half * 32;      // + (j&1)*64
-    const uint32_t o_tmem = tmem_base + lane_base + 384 + half * 64;
+    const uint32_t s_tmem = tmem_base + lane_base + grp * 128;
+    const uint32_t p_tmem = tmem_base + lane_base + 256 + grp * 64;
+    const uint32_t o_tmem = tmem_base + lane_base + 384;
     const float sl2 = a.scale * 1.4426950408889634f;
-    float m, l = 0.f, alpha = 1.0f;
-    bool need = false;
+    float* m_box = xchg;                 // [parity][row]: m(j) of the tile with that parity
+    float* l_box = xchg + 2 * 128;       // [group][row]: partial row sums at the end
+    float m_mine = -INFINITY, l = 0.f;   // the maximum this thread's partial sum is relative to
     const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
@@ -202,78 +217,54 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     tacc[slot] += _t - tc0;                \
     tc0 = _t;                              \
   }
+    if (timed) tc0 = clock64();
 
-    auto mask_tail = [&](uint32_t (&t)[64], int valid) {   // valid = number of in-range keys among this thread's 64
-      if (valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) t[i] = (i < valid) ? t[i] : 0xff800000u;
-      }
-    };
-    // row maximum over both halves: partial maxima meet in shared memory, one 64-thread barrier per warp pair
-    auto row_max = [&](float mine, int buf) {
-      xchg[(buf * 2 + half) * 128 + r] = mine;
-      named_bar_sync(1 + quad, 64);
-      return fmaxf(mine, xchg[(buf * 2 + (half ^ 1)) * 128 + r]);
-    };
-    auto exp_pair = [&](const uint32_t (&cur)[64], uint32_t (&pk)[32], uint64_t (&sum2)[4], int i, uint64_t sl2_2, uint64_t negm_2) {
-      float x0, x1;
-      f2_unpack(f2_fma(f2_pack_bits(cur[2 * i], cur[2 * i + 1]), sl2_2, negm_2), x0, x1);
-      const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-      sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
-      pk[i] = pack_bf16x2(p0, p1);
-    };
-    // `cur` holds this thread's 64 scores of tile j; m / alpha / need are already decided for it
-    auto step = [&](uint32_t (&cur)[64], uint32_t (&nxt)[64], int j) {
-      const bool has_next = j + 1 < n_tiles;
-      if (has_next) {
-        mbar_wait(&bars[S_FULL + ((j + 1) & 1)], ((j + 1) >> 1) & 1, 60);
-        tc_fence_after();
-        tmem_ld_32x32(s_tmem + ((j + 1) & 1) * 128, *reinterpret_cast<uint32_t(*)[32]>(&nxt[0]));
-        tmem_ld_32x32(s_tmem + ((j + 1) & 1) * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&nxt[32]));
-      }
+    for (int j = grp; j < n_tiles; j += 2) {
+      const int it = j >> 1;   // this group's iteration = phase index of its barriers
+      const int valid = a.Lk - j * BKV;
+      mbar_wait(&bars[S_FULL + grp], it & 1, 60 + grp);
+      tc_fence_after();
       CE_TICK(0)
-      const float neg_m = -m;
-      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
-      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[32];
+      uint32_t s[128];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) exp_pair(cur, pk, sum2, i, sl2_2, negm_2);
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[S_FREE + grp]);  // the buffer may take S(j+2)
       CE_TICK(1)
+      if (valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
+      }
       float mx8[8];
-      if (has_next) {
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars[S_FREE + ((j + 1) & 1)]);  // the buffer may take S(j+3)
-        mask_tail(nxt, a.Lk - (j + 1) * BKV - half * 64);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(nxt[i]);
-      }
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
+      const float mx = sl2 * fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       CE_TICK(2)
-#pragma unroll
-      for (int i = 16; i < 32; ++i) {
-        exp_pair(cur, pk, sum2, i, sl2_2, negm_2);
-        if (has_next && i >= 18) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 8 + (i - 18) * 4 + e;
-            mx8[c & 7] = fmaxf(mx8[c & 7], __uint_as_float(nxt[c]));
-          }
-        }
+      // ---- decide m(j) from m(j-1) (the only serial step between consecutive tiles) and publish it
+      float m_prev = -INFINITY;
+      if (j > 0) {
+        mbar_wait(&bars[M_PUB + (grp ^ 1)], ((j - 1) >> 1) & 1, 64 + grp);
+        m_prev = m_box[(grp ^ 1) * 128 + r];
       }
-      {
-        float a0, a1, b0, b1;
-        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
-        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
-        l = fmaf(l, alpha, (a0 + a1) + (b0 + b1));  // old sum moves to the new reference (alpha = 1 unless the max jumped)
+      const bool need = j > 0 && mx > m_prev + RESCALE_THRESHOLD;
+      const float m = (j == 0 || need) ? mx : m_prev;
+      m_box[grp * 128 + r] = m;
+      mbar_arrive(&bars[M_PUB + grp]);   // release: the store above is visible to the waiting group
+      if (m != m_mine) {                 // bring this thread's partial sum to the new reference (first tile: l = 0)
+        l *= fast_exp2(m_mine - m);
+        m_mine = m;
       }
       CE_TICK(3)
-      // P buffer j&1 was last read by P.V(j-2) (one PV_DONE barrier per buffer: a wait never lags its barrier by two phases)
-      if (j >= 2) mbar_wait(&bars[PV_DONE + (j & 1)], ((j - 2) >> 1) & 1, 70);
       if (__any_sync(0xffffffffu, need)) {
-        mbar_wait(&bars[PV_DONE + ((j - 1) & 1)], ((j - 1) >> 1) & 1, 72);  // O still receives P.V(j-1)
+        // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
+        mbar_wait(&bars[PV_DONE + (grp ^ 1)], ((j - 1) >> 1) & 1, 72 + grp);
         tc_fence_after();
+        const float alpha = need ? fast_exp2(m_prev - m) : 1.0f;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
           tmem_ld_32x32(o_tmem + c * 32, o);
           tmem_ld_wait();
@@ -282,78 +273,65 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tmem_st_32x32(o_tmem + c * 32, o);
         }
       }
+      const float neg_m = -m;
+      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float x0, x1;
+        f2_unpack(f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2), x0, x1);
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+        sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
+        f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
+      // this group's P buffer was last read by P.V(j-2)
+      if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
       tc_fence_after();
-      tmem_st_32x32(p_tmem + (j & 1) * 64, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-      float mxp = 0.f;
-      if (has_next)
-        mxp = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      tmem_st_32x32(p_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      tmem_st_32x32(p_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bars[P_FULL + (j & 1)]);
-      // reference for tile j+1 (identical in both threads of the row)
-      alpha = 1.0f;
-      need = false;
-      if (has_next) {
-        const float mx = sl2 * row_max(mxp, (j + 1) & 1);
-        need = mx > m + RESCALE_THRESHOLD;
-        if (need) {
-          alpha = fast_exp2(m - mx);
-          m = mx;
-        }
-      }
+      mbar_arrive(&bars[P_FULL + grp]);
       CE_TICK(4)
-    };
-
-    uint32_t sA[64], sB[64];
-    mbar_wait(&bars[S_FULL + 0], 0, 60);
-    tc_fence_after();
-    tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sA[0]));
-    tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sA[32]));
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(&bars[S_FREE + 0]);
-    mask_tail(sA, a.Lk - half * 64);
-    {
-      float mx8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sA[i]);
-#pragma unroll
-      for (int i = 8; i < 64; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sA[i]));
-      m = sl2 * row_max(fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))), 0);
-    }
-    if (timed) tc0 = clock64();
-    for (int j = 0; j < n_tiles; j += 2) {
-      step(sA, sB, j);
-      if (j + 1 < n_tiles) step(sB, sA, j + 1);
     }
     if (timed) {
       for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
-      a.timing[5] = n_tiles;
+      a.timing[5] = (n_tiles + 1) / 2;
     }
 
-    // ---- total row sum, normalise and store this thread's 64 output columns
-    // (the exchange buffer NOT used by the last row-max exchange: last written two barriers ago)
-    const int lb = n_tiles & 1;
-    xchg[(lb * 2 + half) * 128 + r] = l;
+    // ---- combine the two partial row sums at the final maximum; group A normalises and stores the row
+    const int last = n_tiles - 1;
+    mbar_wait(&bars[M_PUB + (last & 1)], (last >> 1) & 1, 66 + grp);
+    const float m_final = m_box[(last & 1) * 128 + r];
+    l_box[grp * 128 + r] = l * fast_exp2(m_mine - m_final);   // a group that saw no tile: l = 0, m_mine = -inf -> 0 * 0
     named_bar_sync(1 + quad, 64);
-    const float inv = 1.0f / (l + xchg[(lb * 2 + (half ^ 1)) * 128 + r]);
-    mbar_wait(&bars[PV_DONE + ((n_tiles - 1) & 1)], ((n_tiles - 1) >> 1) & 1, 80);  // commits complete in issue order
-    tc_fence_after();
-    const int row = q0 + r;
-    bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD + half * 64;
+    if (grp == 0) {
+      const float inv = 1.0f / (l_box[r] + l_box[128 + r]);
+      mbar_wait(&bars[PV_DONE + (last & 1)], (last >> 1) & 1, 80);  // commits complete in issue order
+      tc_fence_after();
+      const int row = q0 + r;
+      bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(o_tmem + c * 32, o);
-      tmem_ld_wait();
-      if (row < a.Lq) {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(o_tmem + c * 32, o);
+        tmem_ld_wait();
+        if (row < a.Lq) {
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
-          float y[8];
+          for (int v4 = 0; v4 < 4; ++v4) {
+            float y[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[v4 * 8 + i]) * inv;
-          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) =
-              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[v4 * 8 + i]) * inv;
+            *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          }
         }
       }
     }

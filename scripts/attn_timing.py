@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 t = buf.cpu().tolist()
 ver = os.environ.get("CE_ATTN_V2", "2")
 v2 = ver != "0"
-names = (["wait S(j+1) + issue ld", "exp first half", "ld wait + free S", "exp second half + max(j+1)", "wait PV / store P / arrive / row-max exchange"] if ver == "4" else
+names = (["wait S", "ld S + free buffer", "max", "wait m(j-1), decide, publish m(j)", "(rescale) exp, store P, arrive"] if ver == "4" else
          ["wait S", "ld S", "max", "rescale, exp of keys 0-79, publish P[0:64)", "exp of keys 80-127, publish P[64:128)"]) if v2 else ["wait S", "ld S", "max+decide", "exp+pack", "wait PV(t-1)/rescale", "store P + arrive"]
 n = t[5] if v2 else t[6]
 print("kernel:", ("attention4 (cluster)" if ver == "4" else "attention2 (v2)") if v2 else "attention (v1)", "tiles of this group:", n)
