@@ -26,8 +26,8 @@ namespace {
 constexpr int HD = 128;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int NK = 4;  // K ring depth (S is issued two tiles ahead of the softmax)
-constexpr int NV = 2;  // V ring depth
+constexpr int NK = 3;  // K ring depth (S is issued two tiles ahead of the softmax)
+constexpr int NV = 3;  // V ring depth (a slot is refilled only after BOTH CTAs' P.V has read it)
 constexpr int ATTN4_THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;    // one 64-wide head-dim half of a tile (128 rows x 128 B)
@@ -258,6 +258,10 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         m_mine = m;
       }
       CE_TICK(3)
+      // This group's P buffer was last read by P.V(j-2).  Waiting for it HERE (not just before the P store) also keeps the wait
+      // on the other group's PV_DONE barrier below within one phase of that barrier: commits complete in issue order, so once
+      // P.V(j-2) has landed P.V(j-3) has too, and a parity wait for P.V(j-1) cannot alias an older phase.
+      if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
       if (__any_sync(0xffffffffu, need)) {
         // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
         mbar_wait(&bars[PV_DONE + (grp ^ 1)], ((j - 1) >> 1) & 1, 72 + grp);
@@ -291,8 +295,6 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
-      // this group's P buffer was last read by P.V(j-2)
-      if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
       tc_fence_after();
       tmem_st_32x32(p_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32(p_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
