@@ -277,6 +277,9 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tmem_st_32x32(o_tmem + c * 32, o);
         }
       }
+      // Start group B's first exp phase when group A's first one ends: the two warps of a scheduler then alternate between the
+      // MUFU-bound phase and the latency-bound phases (TMEM load, max, decide, P store) instead of contending in lockstep.
+      if (j == 1) mbar_wait(&bars[P_FULL + 0], 0, 68);
       const float neg_m = -m;
       const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
