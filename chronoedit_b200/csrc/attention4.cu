@@ -209,7 +209,7 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     float* l_box = xchg + 2 * 128;       // [group][row]: partial row sums at the end
     float m_mine = -INFINITY, l = 0.f;   // the maximum this thread's partial sum is relative to
     const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
-    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
 #define CE_TICK(slot)                      \
   if (timed) {                             \
@@ -262,6 +262,7 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       // on the other group's PV_DONE barrier below within one phase of that barrier: commits complete in issue order, so once
       // P.V(j-2) has landed P.V(j-3) has too, and a parity wait for P.V(j-1) cannot alias an older phase.
       if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
+      CE_TICK(4)
       if (__any_sync(0xffffffffu, need)) {
         // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
         mbar_wait(&bars[PV_DONE + (grp ^ 1)], ((j - 1) >> 1) & 1, 72 + grp);
@@ -304,11 +305,11 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + grp]);
-      CE_TICK(4)
+      CE_TICK(5)
     }
     if (timed) {
-      for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
-      a.timing[5] = (n_tiles + 1) / 2;
+      for (int i = 0; i < 6; ++i) a.timing[i] = tacc[i];
+      a.timing[6] = (n_tiles + 1) / 2;
     }
 
     // ---- combine the two partial row sums at the final maximum; group A normalises and stores the row
