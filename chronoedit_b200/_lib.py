@@ -76,6 +76,7 @@ SIGNATURES = {
                                c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ce_attention_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_float, c_int, c_void_p]),
+    "ce_debug_attention_kernel": (c_int, [c_int]),
     "ce_debug_attention_timing": (c_int, [c_void_p]),
     "ce_attention_dual_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -28,5 +28,6 @@ struct AttnArgs {
 };
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
+void set_attention_kernel(int version);  // -1 default / environment, 0, 2, 5 (see attention.cu)
 
 }  // namespace ce

@@ -3,7 +3,7 @@
 //                        B operand K_j is split across the pair (each SM holds 64 of the 128 keys: 16 KB instead of 32 KB)
 //   O += [P0;P1] V_j     P read from each SM's TMEM, V_j split across the pair along the head dimension (64 of 128 dims each)
 // Per SM and key tile the shared memory sees 32 KB of Q + 16 KB of K + 16 KB of V operand reads and 32 KB of TMA fill =
-// 96 KB, against 128 KB (attention2.cu) and 160 KB (multicast variant, attention4.cu): SS MMAs at M128 x N128 x K16 already
+// 96 KB, against 128 KB in attention2.cu (and 160 KB for a TMA-multicast variant of this kernel that was measured and dropped): SS MMAs at M128 x N128 x K16 already
 // consume the SM's full 128 B/clk of shared-memory bandwidth, so this is what decides whether the tensor pipe can stay busy.
 // Each CTA owns ONE 128-query tile and all 512 TMEM columns of its SM:
 //     S0 [0,128)  S1 [128,256)   score buffers of the even / odd key tiles
@@ -11,10 +11,20 @@
 //     O  [384,512)               ONE accumulator
 // 384 threads per CTA: warp 0 TMA producer (its halves of K/V, its Q), warp 1 MMA issuer (leader CTA only, event driven),
 // warps 4-7 softmax group A = even key tiles, warps 8-11 group B = odd key tiles, one thread per query row.  Both groups
-// feed the same accumulator and share the running row maximum through a per-row mailbox (see attention4.cu for the
-// protocol: decide m(j) from m(j-1), publish, lazily rescale O after P.V(j-1)).
+// feed the SAME accumulator, so they share the running row maximum: the thread that handles tile j reads m(j-1) from a
+// per-row mailbox in shared memory (published by the other group right after its max phase), decides m(j) with the usual
+// lazy threshold, publishes it, and -- in the rare case of a jump -- rescales O itself once P.V(j-1) has completed.  Only
+// this short decide step is serial; the long phases (TMEM load, row max, 128 exp2, P store) of consecutive tiles overlap.
+// Each thread keeps the partial row sum of its own tiles relative to the maximum it used last; the two partial sums are
+// brought to the final maximum and added at the end.  Per row this is the same sequence of operations as attention2.cu
+// (same threshold decisions, same bf16 P).
 // Barriers that gather BOTH CTAs (operands landed, S consumed, P published) live in the leader; completion of the MMAs is
 // multicast to both CTAs with tcgen05.commit.
+//
+// STATUS: parity-green (tests/test_gpu_ops.py::test_attention_cluster_kernel*) but NOT the default: 1018-1043 TFLOP/s against
+// 1123 for attention2.cu.  scripts/attn_timing.py shows each group waiting ~1050 cycles per tile for P.V(j-2), i.e. P.V lands
+// ~2300 cycles after P is published although the tensor pipe is only 50 % busy; until that latency is understood the serial
+// chain of attention2.cu is simply traded for another one.  Selected with CE_ATTN_V2=5 or ce_debug_attention_kernel(5).
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).
 #include <cstdlib>

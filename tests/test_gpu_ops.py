@@ -155,6 +155,10 @@ def test_attention_cross(Lk, acc):
 def test_attention_rows_sum_property():
     """Full-size property (L = 7200, the 720p/2-frame token count): with V = 1 the output of softmax(QK^T)V is exactly
     the softmax row sum = 1, whatever Q and K are."""
+    _rows_sum_property()
+
+
+def _rows_sum_property():
     L = _lib()
     lib = L.lib()
     B, H, Lq, hd = 1, 2, 7200, 128
@@ -167,6 +171,22 @@ def test_attention_rows_sum_property():
     L.check(lib.ce_attention_bf16(L.ptr(q), D, L.ptr(k), D, L.ptr(v), D, L.ptr(out), D, B, H, Lq, Lq, 1.0 / math.sqrt(hd), 0, L.current_stream()))
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float(), torch.ones_like(out, dtype=torch.float32), rtol=0, atol=2 ** -7)
+
+
+@gpu
+@pytest.mark.parametrize("version", [5, 0])
+def test_attention_alternative_kernels(version):
+    """The non-default self-attention kernels (5: cta_group::2 cluster kernel with two softmax groups feeding one accumulator,
+    0: single-tile kernel) against the same oracle comparisons and the full-size row-sum property -- the latter has thousands of
+    lazy-rescale events (scores scaled x2), which is what exercises the shared-running-max protocol of kernel 5."""
+    L = _lib()
+    L.check(L.lib().ce_debug_attention_kernel(version))
+    try:
+        for (B, H, Lq, Lk) in [(1, 2, 256, 384), (2, 3, 300, 300), (1, 2, 2048, 2048), (1, 1, 384, 257), (1, 2, 1000, 129 + 256)]:
+            run_attention(B, H, Lq, Lk, seed=Lq + Lk + version)
+        _rows_sum_property()
+    finally:
+        L.check(L.lib().ce_debug_attention_kernel(-1))
 
 
 @gpu
