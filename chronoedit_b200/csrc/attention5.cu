@@ -185,7 +185,6 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                                  umma_desc_kmajor_sw128(k_addr + (kk >> 2) * KPART_BYTES) + 2 * (kk & 3), IDESC_S, kk != 0);
               umma_commit_2sm(&bars[S_FULL + (j & 1)], BOTH_CTAS);
               umma_commit_2sm(&bars[K_EMPTY + j % NK], BOTH_CTAS);
-              if (dbg && j == DBG_TILE + 2) a.timing[12] = clock64();
               ++s_next;
               progress = true;
             }
@@ -195,11 +194,11 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             const int k = pv_next;
             const bool p_ok = k < s_next && mbar_test_wait(&bars[P_FULL + (k & 1)], (k >> 1) & 1);
             if (dbg && k == DBG_TILE && p_ok && !dbg_seen) {   // profiling aid: when did the issuer first see P(k)?
-              a.timing[9] = clock64();
+              a.timing[12] = clock64();
               dbg_seen = true;
             }
             if (p_ok && mbar_test_wait(&bars[V_FULL + k % NV], (k / NV) & 1)) {
-              if (dbg && k == DBG_TILE) a.timing[10] = clock64();
+              if (dbg && k == DBG_TILE) a.timing[13] = clock64();
               tc_fence_after();
               const uint32_t v_addr = smem_u32(smem + Smem5::v + (k % NV) * KV_BYTES);
               const uint32_t p_tm = tmem_base + 256 + (k & 1) * 64;  // packed bf16: 8 columns per K=16 step
@@ -292,9 +291,8 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       // This group's P buffer was last read by P.V(j-2).  Waiting for it HERE (not just before the P store) also keeps the wait
       // on the other group's PV_DONE barrier below within one phase of that barrier: commits complete in issue order, so once
       // P.V(j-2) has landed P.V(j-3) has too, and a parity wait for P.V(j-1) cannot alias an older phase.
-      if (timed && j == DBG_TILE + 2) a.timing[13] = clock64();
       if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
-      if (timed && j == DBG_TILE + 2) a.timing[11] = clock64();
+      if (a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j == DBG_TILE && (quad == 0 || quad == 3)) a.timing[14 + (quad == 3)] = clock64();
       CE_TICK(4)
       if (__any_sync(0xffffffffu, need)) {
         // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
@@ -339,7 +337,7 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&bars[P_FULL + grp], LEADER);
-      if (timed && j == DBG_TILE) a.timing[8] = clock64();
+      if (a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j == DBG_TILE) a.timing[8 + quad] = clock64();   // arrival of each warp of group A
       if (j == 0) mbar_arrive(&bars[STAGGER]);
       CE_TICK(5)
     }

@@ -26,5 +26,5 @@ for nm, c in zip(names, t):
 print(f"  {'total':28s} {sum(t[:len(names)]) / max(n,1):9.1f} cycles/tile")
 if ver == "5" and t[8]:
     t0 = t[8]
-    print(f"life of P(24)/P.V(24) in block 0 (cycles after the timed thread published P(24)): issuer saw P_FULL +{t[9]-t0}, issued P.V +{t[10]-t0}, "
-          f"S(26) issued +{t[12]-t0}, group reached its P.V(24) wait +{t[13]-t0}, wait returned +{t[11]-t0}")
+    print("tile 24, block 0, group A (cycles relative to warp 4 publishing P): warps 4..7 published P at", [t[8 + i] - t0 for i in range(4)],
+          "| warps 4 / 7 started their exp phase at", t[14] - t0, t[15] - t0, "| issuer saw P_FULL", t[12] - t0, "issued P.V", t[13] - t0)
