@@ -400,9 +400,14 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_per_step": e2e_wall_ms / e2e_steps},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all Linear layers)",
+                "bound": "tensor", "kernel": "gemm_bf16_2cta_kernel / gemm_bf16_kernel (tcgen05, all Linear layers)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "peak_source": peak_src + " bf16_tflops_sustained",
-                "traffic": None, "launches": prof["count"][0], "ms_total": prof["ms"][0],
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at the QKV shape (M=14400, N=15360, K=5120)
+                # from the committed ncu --set full capture profiles/r01w_ncu_gemm.csv; algorithmic operand bytes of that launch
+                # = (M*K + N*K + M*N)*2 = 0.747e9 (each L2 die fetches its own copy of A and W)
+                "traffic": 1.401254e9 + 0.430177e9, "traffic_launch": "gemm_bf16_2cta_kernel M=14400 N=15360 K=5120 (profiles/r01w_ncu_gemm.csv)",
+                "algorithmic_bytes_of_that_launch": (14400 * 5120 + 15360 * 5120 + 14400 * 15360) * 2,
+                "launches": prof["count"][0], "ms_total": prof["ms"][0],
                 "share_of_kernel_time": prof["ms"][0] / kernel_ms if kernel_ms else None,
                 "attention": {"achieved": attn_tf, "frac": attn_tf / peak_tf, "ms_total": prof["ms"][1], "launches": prof["count"][1]},
                 "rows_ms_total": prof["ms"][2], "other_ms_total": prof["ms"][3],
