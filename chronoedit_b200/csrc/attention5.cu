@@ -21,10 +21,12 @@
 // Barriers that gather BOTH CTAs (operands landed, S consumed, P published) live in the leader; completion of the MMAs is
 // multicast to both CTAs with tcgen05.commit.
 //
-// STATUS: parity-green (tests/test_gpu_ops.py::test_attention_cluster_kernel*) but NOT the default: 1018-1043 TFLOP/s against
-// 1123 for attention2.cu.  scripts/attn_timing.py shows each group waiting ~1050 cycles per tile for P.V(j-2), i.e. P.V lands
-// ~2300 cycles after P is published although the tensor pipe is only 50 % busy; until that latency is understood the serial
-// chain of attention2.cu is simply traded for another one.  Selected with CE_ATTN_V2=5 or ce_debug_attention_kernel(5).
+// STATUS: parity-green (tests/test_gpu_ops.py::test_attention_alternative_kernels) but NOT the default: 970-1040 TFLOP/s
+// against 1123 for attention2.cu.  scripts/attn_timing.py (per-warp timestamps of tile DBG_TILE) shows each group waiting
+// ~1000 cycles per tile for P.V(j-2): the peer CTA's "P published" arrivals reach the leader ~1100 cycles after the leader's
+// own, so P.V is issued late although the tensor pipe is only 50 % busy -- the per-tile cross-CTA handshakes are in the
+// loop and two S / two P buffers are all the TMEM has to hide them.  Selected with CE_ATTN_V2=5 or
+// ce_debug_attention_kernel(5).
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).
 #include <cstdlib>
