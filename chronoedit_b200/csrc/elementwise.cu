@@ -1,8 +1,6 @@
 // HBM-bound row kernels of the DiT path: fp32 LayerNorm + adaLN modulate, RMSNorm-across-heads + 3D RoPE,
 // patchify / unpatchify, and the tiny-M Linear layers of the time embedder.  All are coalesced 16-byte
 // accesses with one CTA per token row (rows >> SM count), statistics in fp32 via warp shuffles.
-#include <cstdlib>
-
 #include "elementwise.cuh"
 
 namespace ce {
@@ -34,8 +32,8 @@ __device__ __forceinline__ float2 pair_sum(float a, float b, float2* part) {
   return make_float2(a + o.x, b + o.y);
 }
 
-template <int HV, int OCC>
-__global__ void __launch_bounds__(ROW_THREADS, OCC)
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
                  const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
                  const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
@@ -119,8 +117,8 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int HV, int OCC>
-__global__ void __launch_bounds__(ROW_THREADS, OCC)
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
   __shared__ float2 part[ROW_THREADS / 32];
@@ -290,16 +288,6 @@ __global__ void add_table_kernel(const float* __restrict__ table, int table_rows
 
 }  // namespace
 
-// developer knob CE_ROW_OCC: 2 (default: ~120 registers, no spills) or 3 (80 registers, a few spilled values) CTAs per SM for the
-// D = 5120 row kernels
-static int row_occupancy() {
-  static const int v = [] {
-    const char* e = getenv("CE_ROW_OCC");
-    return (e && e[0] == '3') ? 3 : 2;
-  }();
-  return v;
-}
-
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
                      cudaStream_t stream, int scale_is_1p) {
@@ -310,13 +298,11 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, 
   if (rows_per_batch <= 0) rows_per_batch = rows;
   const int grid = (rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64);
   const int nvec = D / 8;
-#define CE_LN(V, O) layernorm_kernel<V, O><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p)
-  if (nvec <= 128) CE_LN(2, 2);
-  else if (nvec <= 256) CE_LN(4, 2);
-  else if (nvec <= 640) {   // D = 5120 (the 14B width): resident CTAs per SM is the lever (bytes in flight), see row_occupancy()
-    if (row_occupancy() == 3) CE_LN(10, 3);
-    else CE_LN(10, 2);
-  } else CE_LN(16, 2);
+#define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p)
+  if (nvec <= 128) CE_LN(2);
+  else if (nvec <= 256) CE_LN(4);
+  else if (nvec <= 640) CE_LN(10);
+  else CE_LN(16);
 #undef CE_LN
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
@@ -329,13 +315,11 @@ int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16
   if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm: rope table / head_dim");
   const int grid = (rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64);
   const int nvec = D / 8;
-#define CE_RMS(V, O) rmsnorm_rope_kernel<V, O><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim)
-  if (nvec <= 128) CE_RMS(2, 2);
-  else if (nvec <= 256) CE_RMS(4, 2);
-  else if (nvec <= 640) {
-    if (row_occupancy() == 3) CE_RMS(10, 3);
-    else CE_RMS(10, 2);
-  } else CE_RMS(16, 2);
+#define CE_RMS(V) rmsnorm_rope_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim)
+  if (nvec <= 128) CE_RMS(2);
+  else if (nvec <= 256) CE_RMS(4);
+  else if (nvec <= 640) CE_RMS(10);
+  else CE_RMS(16);
 #undef CE_RMS
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
