@@ -358,6 +358,65 @@ class ChronoEditTransformer3DModel(nn.Module):
     def launches_per_forward(self) -> int:
         return int(_lib.lib().ce_dit_last_launch_count(self._handle)) if self._handle else 0
 
+    # ------------------------------------------------------------------------------------------ LoRA
+    # (original Wan module name -> diffusers name) pairs of the reference's own converter, chronoedit/_src/models/utils.py:112-190
+    _WAN_TO_DIFFUSERS = (("self_attn.q", "attn1.to_q"), ("self_attn.k", "attn1.to_k"), ("self_attn.v", "attn1.to_v"),
+                         ("self_attn.o", "attn1.to_out.0"), ("cross_attn.q", "attn2.to_q"), ("cross_attn.k_img", "attn2.add_k_proj"),
+                         ("cross_attn.v_img", "attn2.add_v_proj"), ("cross_attn.k", "attn2.to_k"), ("cross_attn.v", "attn2.to_v"),
+                         ("cross_attn.o", "attn2.to_out.0"), ("ffn.0", "ffn.net.0.proj"), ("ffn.2", "ffn.net.2"))
+
+    @torch.no_grad()
+    def fuse_lora(self, lora_state_dict: Dict[str, torch.Tensor], lora_scale: float = 1.0, adapter_name: Optional[str] = None) -> int:
+        """`pipe.load_lora_weights(path); pipe.fuse_lora(lora_scale=s)` (run_inference_diffusers.py:369-376) for this module:
+        W += (B @ A) * (s * alpha / r), in place and in the weight dtype, which is PEFT's merge arithmetic.  The kernels see
+        the result without repacking because the fused QKV buffers are views of the same storage.
+
+        Keys: diffusers / PEFT style `[transformer.]blocks.N.attn1.to_q.lora_A[.adapter].weight` (+ `lora_B`, optional
+        `.alpha`), or the original Wan style the in-tree loader converts (`[diffusion_model.]blocks.N.self_attn.q.lora_down|lora_A
+        .weight`, `lora_up|lora_B`, `.alpha`; chronoedit/_src/models/utils.py:66-190, wan_t2v_model.py:385-391).  `diff` /
+        `diff_b` entries (norm / bias deltas the reference converter drops or treats as lora_bias) are rejected.  One-time
+        weight preparation with torch matmuls; not on the per-step path.  Returns the number of weights updated."""
+        params = dict(self.named_parameters())
+        pairs: Dict[str, Dict[str, torch.Tensor]] = {}
+        for key, val in lora_state_dict.items():
+            k = key
+            for pre in ("transformer.", "diffusion_model."):
+                if k.startswith(pre):
+                    k = k[len(pre):]
+            if k.endswith((".diff", ".diff_b")):
+                raise CEError(f"fuse_lora: '{key}' is a weight/bias delta, not a low-rank pair; not supported")
+            if adapter_name is not None:
+                k = k.replace(f".{adapter_name}.", ".")
+            k = k.replace(".lora_down.", ".lora_A.").replace(".lora_up.", ".lora_B.")
+            if k.endswith(".alpha"):
+                mod, kind = k[: -len(".alpha")], "alpha"
+            elif k.endswith(".lora_A.weight"):
+                mod, kind = k[: -len(".lora_A.weight")], "A"
+            elif k.endswith(".lora_B.weight"):
+                mod, kind = k[: -len(".lora_B.weight")], "B"
+            else:
+                raise CEError(f"fuse_lora: unrecognised key '{key}'")
+            for wan, dif in self._WAN_TO_DIFFUSERS:
+                if mod.endswith("." + wan):
+                    mod = mod[: -len(wan)] + dif
+                    break
+            pairs.setdefault(mod, {})[kind] = val
+        n = 0
+        for mod, d in pairs.items():
+            if "A" not in d or "B" not in d:
+                raise CEError(f"fuse_lora: '{mod}' needs both lora_A and lora_B")
+            w = params.get(mod + ".weight")
+            if w is None:
+                raise CEError(f"fuse_lora: no parameter '{mod}.weight' in this model")
+            A, B = d["A"].to(w.device, w.dtype), d["B"].to(w.device, w.dtype)
+            r = A.shape[0]
+            if A.shape != (r, w.shape[1]) or B.shape != (w.shape[0], r):
+                raise CEError(f"fuse_lora: shapes of '{mod}' do not match: A {tuple(A.shape)} B {tuple(B.shape)} W {tuple(w.shape)}")
+            alpha = float(d["alpha"]) if "alpha" in d else float(r)
+            w.data += (B @ A) * (lora_scale * alpha / r)   # peft LoraLayer.get_delta_weight / merge
+            n += 1
+        return n
+
     # ------------------------------------------------------------------------------------------ loading
     @classmethod
     def from_config(cls, config: Dict[str, Any], **kw) -> "ChronoEditTransformer3DModel":

@@ -135,3 +135,33 @@ def test_dit_full_width_single_layer_at_720p():
     assert torch.isfinite(out).all()
     assert e_our.mean() <= 1.25 * e_ref.mean(), f"mean err {e_our.mean():.3g} vs reference bf16 {e_ref.mean():.3g}"
     assert e_our.max() <= 2.0 * e_ref.max(), f"max err {e_our.max():.3g} vs reference bf16 {e_ref.max():.3g}"
+
+
+@gpu
+def test_dit_forward_after_lora_fuse():
+    """`fuse_lora` updates the named parameters in place; the kernels read fused QKV / KV buffers that are views of the same
+    storage, so the next forward must equal the oracle run on the merged weights (the 8-step distilled LoRA flow,
+    run_inference_diffusers.py:369-376)."""
+    from oracle import cases, dit_oracle
+
+    case = cases.DIT_CASES["tiny_t2"]
+    m = _build(case)
+    x, t, text, img = cases.dit_inputs(case)
+    base = m(x.cuda(), t.cuda(), text.cuda(), img.cuda(), return_dict=False)[0].float().cpu()   # packs the weights
+    g = torch.Generator().manual_seed(7)
+    lora = {}
+    for n, p in m.named_parameters():
+        if n.endswith(".weight") and any(s in n for s in ("attn1.to_", "attn2.to_", "attn2.add_", "ffn.net")) and "norm" not in n:
+            mod = n[: -len(".weight")]
+            lora[f"transformer.{mod}.lora_A.weight"] = (torch.randn(8, p.shape[1], generator=g) * 0.2).bfloat16()
+            lora[f"transformer.{mod}.lora_B.weight"] = (torch.randn(p.shape[0], 8, generator=g) * 0.2).bfloat16()
+    assert m.fuse_lora(lora, lora_scale=1.0) == len(lora) // 2
+    out = m(x.cuda(), t.cuda(), text.cuda(), img.cuda(), return_dict=False)[0].float().cpu()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sd32 = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = dit_oracle.dit_forward(sd32, case.cfg, x, t, text, img)
+        ref16 = dit_oracle.dit_forward(sd, case.cfg, x.bfloat16(), t, text.bfloat16(), img.bfloat16()).float()
+    assert (out - base).abs().mean() > 10 * (ref16 - ref32).abs().mean(), "the LoRA did not change the output"
+    e_ref, e_our = (ref16 - ref32).abs(), (out - ref32).abs()
+    assert e_our.mean() <= 1.25 * e_ref.mean() and e_our.max() <= 2.0 * e_ref.max()
