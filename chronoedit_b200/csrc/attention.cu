@@ -131,7 +131,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         }
         if (progress) {
           idle = 0;
-        } else if (poll_backoff(a.poll_ns), (++idle & 0x3FF) == 0) {
+        } else if ((++idle & 0xFFF) == 0) {
           if (t_start == 0) t_start = global_timer_ns();
           else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
             printf("[chronoedit_b200] attention producer stalled: block=(%d,%d,%d) k=%d,%d v=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z,
@@ -202,7 +202,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         }
         if (progress) {
           idle = 0;
-        } else if (poll_backoff(a.poll_ns), (++idle & 0x3FF) == 0) {
+        } else if ((++idle & 0xFFF) == 0) {
           if (t_start == 0) t_start = global_timer_ns();
           else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
             printf("[chronoedit_b200] attention MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],
@@ -435,13 +435,7 @@ static int attn_version() {
   return v;
 }
 
-int launch_attention(const AttnArgs& a_in, cudaStream_t stream) {
-  AttnArgs a = a_in;
-  static const int poll_ns = [] {   // developer knob; default chosen by A/B on the 14B self-attention shape
-    const char* e = getenv("CE_ATTN_POLL_NS");
-    return e ? atoi(e) : 0;
-  }();
-  a.poll_ns = poll_ns;
+int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
   // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
   if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && attn_version() != 0)

@@ -25,7 +25,6 @@ struct AttnArgs {
   float scale = 0.f;        // 1/sqrt(head_dim)
   long long* timing = nullptr;  // optional [16] device counters: phase cycles of softmax warp 4 lane 0 of block (0,0,0) (profiling aid)
   int accumulate = 0;       // 1: out = bf16(float(bf16(attn)) + float(out))   (image + text cross-attention sum)
-  int poll_ns = 0;          // back-off of the polling producer / issuer threads when nothing is ready (filled in by launch_attention)
 };
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream);

@@ -117,7 +117,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
           if (progress) {
             idle = 0;
-          } else if (poll_backoff(a.poll_ns), (++idle & 0x3FF) == 0) {
+          } else if ((++idle & 0xFFF) == 0) {
             if (t_start == 0) t_start = global_timer_ns();
             else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
               printf("[chronoedit_b200] attention2 producer stalled: block=(%d,%d,%d) k=%d v=%d\n", blockIdx.x, blockIdx.y, blockIdx.z, k_next, v_next);
@@ -194,7 +194,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
           if (progress) {
             idle = 0;
-          } else if (poll_backoff(a.poll_ns), (++idle & 0x3FF) == 0) {
+          } else if ((++idle & 0xFFF) == 0) {
             if (t_start == 0) t_start = global_timer_ns();
             else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
               printf("[chronoedit_b200] attention2 MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],

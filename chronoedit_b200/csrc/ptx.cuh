@@ -77,12 +77,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
-// A thread that polls several barriers shares its scheduler with working warps: every probe is an issue slot taken from them.
-// Backing off for a few dozen ns when nothing was ready gives those slots back at the price of that much reaction latency.
-__device__ __forceinline__ void poll_backoff(int ns) {
-  if (ns > 0) asm volatile("nanosleep.u32 %0;" ::"r"(ns));
-}
-
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
