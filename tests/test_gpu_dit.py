@@ -138,6 +138,40 @@ def test_dit_full_width_single_layer_at_720p():
 
 
 @gpu
+def test_dit_temporal_reasoning_token_count_at_720p():
+    """BASELINE.json configs[2] geometry: 8 latent frames at 720p = 28 800 tokens (RoPE temporal skip table for 8 frames, 225 key
+    tiles per head, workspace sizing), at a width the CPU oracle can follow (dim 256, 2 heads, 2 layers)."""
+    import chronoedit_b200 as ce
+    from oracle import cases, dit_oracle as O
+
+    cfg = O.DiTConfig.tiny()
+    sd32 = O.random_state_dict(cfg, seed=9)
+    sdb = cases.to_bf16_state(sd32)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 36, 8, 90, 160, generator=g)
+    text = torch.randn(1, 512, cfg.text_dim, generator=g)
+    img = torch.randn(1, 257, cfg.image_dim, generator=g)
+    t = torch.tensor([333])
+    m = ce.ChronoEditTransformer3DModel(
+        patch_size=cfg.patch_size, num_attention_heads=cfg.num_attention_heads, attention_head_dim=cfg.attention_head_dim,
+        in_channels=cfg.in_channels, out_channels=cfg.out_channels, text_dim=cfg.text_dim, freq_dim=cfg.freq_dim,
+        ffn_dim=cfg.ffn_dim, num_layers=cfg.num_layers, eps=cfg.eps, image_dim=cfg.image_dim,
+        added_kv_proj_dim=cfg.added_kv_proj_dim, rope_max_seq_len=cfg.rope_max_seq_len,
+        rope_temporal_skip_len=cfg.rope_temporal_skip_len)
+    m.load_state_dict(sdb)
+    m = m.cuda()
+    out = m(x.cuda(), t.cuda(), text.cuda(), img.cuda(), return_dict=False)[0].float().cpu()
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref32 = O.dit_forward(sd32, cfg, x, t, text, img)
+        ref16 = O.dit_forward(sdb, cfg, x.bfloat16(), t, text.bfloat16(), img.bfloat16()).float()
+    e_ref, e_our = (ref16 - ref32).abs(), (out - ref32).abs()
+    assert out.shape == ref32.shape and torch.isfinite(out).all()
+    assert e_our.mean() <= 1.25 * e_ref.mean(), f"mean err {e_our.mean():.3g} vs reference bf16 {e_ref.mean():.3g}"
+    assert e_our.max() <= 2.0 * e_ref.max(), f"max err {e_our.max():.3g} vs reference bf16 {e_ref.max():.3g}"
+
+
+@gpu
 def test_dit_forward_after_lora_fuse():
     """`fuse_lora` updates the named parameters in place; the kernels read fused QKV / KV buffers that are views of the same
     storage, so the next forward must equal the oracle run on the merged weights (the 8-step distilled LoRA flow,
