@@ -50,7 +50,6 @@ constexpr uint32_t KPART_BYTES = 64 * 64 * 2;      // 64 keys x 64 dims: one hea
 constexpr float RESCALE_THRESHOLD = 8.0f;
 constexpr uint16_t BOTH_CTAS = 0x3;
 constexpr uint32_t LEADER = 0;
-constexpr int DBG_TILE = 24;   // profiling aid (ce_debug_attention_timing): the life of P(24) / P.V(24) is timestamped
 
 struct Smem5 {
   static constexpr uint32_t q = 0;
@@ -63,7 +62,7 @@ struct Smem5 {
 static_assert(Smem5::total <= 227 * 1024, "attention5: shared memory budget");
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV, S_FREE = S_FULL + 2,
-       P_FULL = S_FREE + 2, PV_DONE = P_FULL + 2, M_PUB = PV_DONE + 2, STAGGER = M_PUB + 2, NUM_BARS5 = STAGGER + 1 };
+       P_FULL = S_FREE + 2, PV_DONE = P_FULL + 2, M_PUB = PV_DONE + 2, EXP_DONE = M_PUB + 2, NUM_BARS5 = EXP_DONE + 2 };
 static_assert(NUM_BARS5 * 8 + 8 <= 256, "attention5: barrier block");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN5_THREADS, 1)
@@ -91,7 +90,7 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       uint32_t count = 1;                                                        // multicast commits, EMPTY barriers
       if (i == Q_FULL || (i >= K_FULL && i < K_FULL + NK) || (i >= V_FULL && i < V_FULL + NV)) count = 2;   // leader: one producer per CTA
       if (i >= S_FREE && i < P_FULL + 2) count = 8;                              // leader: one arrival per softmax warp of the group, both CTAs
-      if (i >= M_PUB) count = 128;                                               // every thread of one softmax group (incl. STAGGER)
+      if (i >= M_PUB) count = 128;                                               // every thread of one softmax group (M_PUB, EXP_DONE)
       mbar_init(&bars[i], count);
     }
     fence_mbar_init();
@@ -170,8 +169,6 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         int s_next = 0, pv_next = 0;
         uint64_t t_start = 0;
         uint32_t idle = 0;
-        const bool dbg = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-        bool dbg_seen = false;
         while (pv_next < n_tiles) {
           bool progress = false;
           // S(j) -> buffer j&1: free once the group of that parity has pulled S(j-2) into registers (early in its step)
@@ -195,12 +192,7 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           {
             const int k = pv_next;
             const bool p_ok = k < s_next && mbar_test_wait(&bars[P_FULL + (k & 1)], (k >> 1) & 1);
-            if (dbg && k == DBG_TILE && p_ok && !dbg_seen) {   // profiling aid: when did the issuer first see P(k)?
-              a.timing[12] = clock64();
-              dbg_seen = true;
-            }
             if (p_ok && mbar_test_wait(&bars[V_FULL + k % NV], (k / NV) & 1)) {
-              if (dbg && k == DBG_TILE) a.timing[13] = clock64();
               tc_fence_after();
               const uint32_t v_addr = smem_u32(smem + Smem5::v + (k % NV) * KV_BYTES);
               const uint32_t p_tm = tmem_base + 256 + (k & 1) * 64;  // packed bf16: 8 columns per K=16 step
@@ -239,7 +231,9 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     float* m_box = xchg;                 // [parity][row]: m(j) of the tile with that parity
     float* l_box = xchg + 2 * 128;       // [group][row]: partial row sums at the end
     float m_mine = -INFINITY, l = 0.f;   // the maximum this thread's partial sum is relative to
-    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    // profiling aid: phase cycles of warp 4 lane 0 in the leader CTA (slots 0-6) and in its peer (slots 8-14) of cluster 0
+    const bool timed = a.timing != nullptr && blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    const int tslot = blockIdx.x * 8;
     long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
 #define CE_TICK(slot)                      \
@@ -294,7 +288,6 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       // on the other group's PV_DONE barrier below within one phase of that barrier: commits complete in issue order, so once
       // P.V(j-2) has landed P.V(j-3) has too, and a parity wait for P.V(j-1) cannot alias an older phase.
       if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
-      if (a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j == DBG_TILE && (quad == 0 || quad == 3)) a.timing[14 + (quad == 3)] = clock64();
       CE_TICK(4)
       if (__any_sync(0xffffffffu, need)) {
         // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
@@ -311,9 +304,10 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tmem_st_32x32(o_tmem + c * 32, o);
         }
       }
-      // Start group B's first exp phase when group A's first one ends: the two warps of a scheduler then alternate between the
-      // MUFU-bound phase and the latency-bound phases (TMEM load, max, decide, P store) instead of contending in lockstep.
-      if (j == 1) mbar_wait(&bars[STAGGER], 0, 68);
+      // The exp phase is the MUFU-bound one and the two groups share the SM's MUFU: take turns.  Group g may start the
+      // exponentials of tile j once the other group has finished those of tile j-1; its TMEM load, row max, decide step and P
+      // store then overlap the other group's exponentials instead of both groups contending and both idling together.
+      if (j > 0) mbar_wait(&bars[EXP_DONE + (grp ^ 1)], ((j - 1) >> 1) & 1, 68);
       const float neg_m = -m;
       const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
@@ -326,6 +320,7 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
       }
+      mbar_arrive(&bars[EXP_DONE + grp]);
       {
         float a0, a1, b0, b1;
         f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
@@ -339,13 +334,11 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&bars[P_FULL + grp], LEADER);
-      if (a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j == DBG_TILE) a.timing[8 + quad] = clock64();   // arrival of each warp of group A
-      if (j == 0) mbar_arrive(&bars[STAGGER]);
       CE_TICK(5)
     }
     if (timed) {
-      for (int i = 0; i < 6; ++i) a.timing[i] = tacc[i];
-      a.timing[6] = (n_tiles + 1) / 2;
+      for (int i = 0; i < 6; ++i) a.timing[tslot + i] = tacc[i];
+      a.timing[tslot + 6] = (n_tiles + 1) / 2;
     }
 
     // ---- combine the two partial row sums at the final maximum; group A normalises and stores the row

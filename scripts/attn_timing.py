@@ -24,7 +24,8 @@ print("kernel:", ("attention5 (cta_group::2)" if ver == "5" else "attention2 (v2
 for nm, c in zip(names, t):
     print(f"  {nm:28s} {c / max(n,1):9.1f} cycles/tile")
 print(f"  {'total':28s} {sum(t[:len(names)]) / max(n,1):9.1f} cycles/tile")
-if ver == "5" and t[8]:
-    t0 = t[8]
-    print("tile 24, block 0, group A (cycles relative to warp 4 publishing P): warps 4..7 published P at", [t[8 + i] - t0 for i in range(4)],
-          "| warps 4 / 7 started their exp phase at", t[14] - t0, t[15] - t0, "| issuer saw P_FULL", t[12] - t0, "issued P.V", t[13] - t0)
+if ver == "5" and t[14]:
+    print("peer CTA of the same cluster:")
+    for nm, c in zip(names, t[8:14]):
+        print(f"  {nm:28s} {c / max(t[14],1):9.1f} cycles/tile")
+    print(f"  {'total':28s} {sum(t[8:14]) / max(t[14],1):9.1f} cycles/tile")
