@@ -234,7 +234,7 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     // profiling aid: phase cycles of warp 4 lane 0 in the leader CTA (slots 0-6) and in its peer (slots 8-14) of cluster 0
     const bool timed = a.timing != nullptr && blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     const int tslot = blockIdx.x * 8;
-    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
 #define CE_TICK(slot)                      \
   if (timed) {                             \
@@ -284,13 +284,12 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         m_mine = m;
       }
       CE_TICK(3)
-      // This group's P buffer was last read by P.V(j-2).  Waiting for it HERE (not just before the P store) also keeps the wait
-      // on the other group's PV_DONE barrier below within one phase of that barrier: commits complete in issue order, so once
-      // P.V(j-2) has landed P.V(j-3) has too, and a parity wait for P.V(j-1) cannot alias an older phase.
-      if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
       CE_TICK(4)
       if (__any_sync(0xffffffffu, need)) {
-        // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j)
+        // O holds the tiles up to j-1 relative to m(j-1): P.V(j-1) must have landed, P.V(j) waits for this thread's P(j).
+        // The wait on the OTHER group's barrier is only safe within one phase of it: consume this group's own P.V(j-2) first
+        // (commits complete in issue order, so P.V(j-3) has landed too and the parity wait below cannot alias an older phase).
+        if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
         mbar_wait(&bars[PV_DONE + (grp ^ 1)], ((j - 1) >> 1) & 1, 72 + grp);
         tc_fence_after();
         const float alpha = need ? fast_exp2(m_prev - m) : 1.0f;
@@ -327,6 +326,10 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         f2_unpack(f2_add(sum2[2], sum2[3]), b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
+      // this group's P buffer was last read by P.V(j-2): only the STORE needs it, so the cross-CTA round trip of that P.V
+      // (peer's "P published" -> leader issues -> commit multicast back) hides behind this tile's load / max / decide / exp
+      if (j >= 2) mbar_wait(&bars[PV_DONE + grp], (it - 1) & 1, 70 + grp);
+      CE_TICK(5)
       tc_fence_after();
       tmem_st_32x32(p_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32(p_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
@@ -334,11 +337,11 @@ attention5_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&bars[P_FULL + grp], LEADER);
-      CE_TICK(5)
+      CE_TICK(6)
     }
     if (timed) {
-      for (int i = 0; i < 6; ++i) a.timing[tslot + i] = tacc[i];
-      a.timing[tslot + 6] = (n_tiles + 1) / 2;
+      for (int i = 0; i < 7; ++i) a.timing[tslot + i] = tacc[i];
+      a.timing[tslot + 7] = (n_tiles + 1) / 2;
     }
 
     // ---- combine the two partial row sums at the final maximum; group A normalises and stores the row
