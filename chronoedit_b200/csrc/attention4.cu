@@ -146,12 +146,25 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         int s_next = 0, pv_next = 0;
         uint64_t t_start = 0;
         uint32_t idle = 0;
+        const bool dbg = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        bool dbg_s = false, dbg_w = false;
         while (pv_next < n_tiles) {
+          if (dbg && s_next == 26 && !dbg_w) {   // when did S(25) get out of the way?
+            a.timing[11] = clock64();
+            dbg_w = true;
+          }
+          if (dbg && s_next > 26 && a.timing[12] == 0 && mbar_test_wait(&bars[S_FULL + 0], (26 >> 1) & 1)) a.timing[12] = clock64();   // S(26) landed
           bool progress = false;
           // S(j) -> buffer j&1: free once the group of that parity has pulled S(j-2) into registers (early in its step)
           if (s_next < n_tiles) {
             const int j = s_next;
-            if ((j < 2 || mbar_test_wait(&bars[S_FREE + (j & 1)], ((j - 2) >> 1) & 1)) && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+            const bool s_ok = j < 2 || mbar_test_wait(&bars[S_FREE + (j & 1)], ((j - 2) >> 1) & 1);
+            if (dbg && j == 26 && s_ok && !dbg_s) {   // profiling aid: the life of S(26)
+              a.timing[9] = clock64();
+              dbg_s = true;
+            }
+            if (s_ok && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
+              if (dbg && j == 26) a.timing[10] = clock64();
               tc_fence_after();
               const uint32_t k_addr = smem_u32(smem + Smem4::k + (j % NK) * TILE_BYTES);
               const uint32_t d = tmem_base + (j & 1) * 128;
@@ -231,6 +244,7 @@ attention4_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[S_FREE + grp]);  // the buffer may take S(j+2)
+      if (timed && j == 24) a.timing[8] = clock64();
       CE_TICK(1)
       if (valid < BKV) {
 #pragma unroll

@@ -30,3 +30,7 @@ if ver == "5" and t[15]:
     for nm, c in zip(names, t[8:15]):
         print(f"  {nm:28s} {c / max(t[15],1):9.1f} cycles/tile")
     print(f"  {'total':28s} {sum(t[8:15]) / max(t[15],1):9.1f} cycles/tile")
+if ver == "4" and t[8]:
+    t0 = t[8]
+    print(f"life of S(26) in block 0 (cycles after the timed thread released the S buffer of tile 24): issuer reached s_next=26 at +{t[11]-t0}, saw S_FREE +{t[9]-t0}, "
+          f"saw K_FULL and issued +{t[10]-t0}, S(26) landed +{t[12]-t0}")
