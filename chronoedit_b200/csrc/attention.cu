@@ -419,7 +419,6 @@ int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld)
 }  // namespace
 
 int launch_attention2(const AttnArgs& a, cudaStream_t stream);  // attention2.cu
-int launch_attention4(const AttnArgs& a, cudaStream_t stream);  // attention4.cu
 int launch_attention5(const AttnArgs& a, cudaStream_t stream);  // attention5.cu
 
 // Which kernel serves long single-source problems (the self-attention): 2 = attention2.cu (default), 5 = attention5.cu
@@ -431,7 +430,7 @@ static int attn_version() {
   if (g_attn_override >= 0) return g_attn_override;
   static const int v = [] {
     const char* e = getenv("CE_ATTN_V2");
-    return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : (e[0] == '4' ? 4 : 2)));
+    return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : 2));
   }();
   return v;
 }
@@ -440,7 +439,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
   // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
   if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && attn_version() != 0)
-    return attn_version() == 5 ? launch_attention5(a, stream) : (attn_version() == 4 ? launch_attention4(a, stream) : launch_attention2(a, stream));
+    return attn_version() == 5 ? launch_attention5(a, stream) : launch_attention2(a, stream);
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
   CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");

@@ -584,7 +584,7 @@ int ce_debug_attention_timing(long long* buf) {
 // Test / A-B aid: which kernel serves the self-attention from now on (2 default, 5 cta_group::2 cluster kernel, 0 the
 // single-tile kernel of attention.cu; -1 back to the CE_ATTN_V2 / built-in default).
 int ce_debug_attention_kernel(int version) {
-  if (version != -1 && version != 0 && version != 2 && version != 4 && version != 5) return ce::fail(ce::CE_ERR_INVALID, "attention kernel version must be -1, 0, 2, 4 or 5");
+  if (version != -1 && version != 0 && version != 2 && version != 5) return ce::fail(ce::CE_ERR_INVALID, "attention kernel version must be -1, 0, 2 or 5");
   ce::set_attention_kernel(version);
   return CE_OK;
 }

@@ -18,10 +18,9 @@ t = buf.cpu().tolist()
 ver = os.environ.get("CE_ATTN_V2", "2")
 v2 = ver != "0"
 names = (["wait S", "ld S + free buffer", "max", "wait m(j-1), decide, publish m(j)", "(rescale)", "wait exp turn, exp, wait P.V(j-2)", "store P, arrive"] if ver == "5" else
-         ["wait S", "ld S + free buffer", "max", "wait m(j-1), decide, publish m(j)", "-", "wait exp turn, exp, wait P.V(j-2), store P, arrive"] if ver == "4" else
          ["wait S", "ld S", "max", "rescale, exp of keys 0-79, publish P[0:64)", "exp of keys 80-127, publish P[64:128)"]) if v2 else ["wait S", "ld S", "max+decide", "exp+pack", "wait PV(t-1)/rescale", "store P + arrive"]
-n = t[7] if ver == "5" else (t[6] if ver == "4" else (t[5] if v2 else t[6]))
-print("kernel:", ({"5": "attention5 (cta_group::2)", "4": "attention4 (multicast cluster)"}.get(ver, "attention2 (v2)")) if v2 else "attention (v1)", "tiles of this group:", n)
+n = t[7] if ver == "5" else (t[5] if v2 else t[6])
+print("kernel:", ("attention5 (cta_group::2)" if ver == "5" else "attention2 (v2)") if v2 else "attention (v1)", "tiles of this group:", n)
 for nm, c in zip(names, t):
     print(f"  {nm:28s} {c / max(n,1):9.1f} cycles/tile")
 print(f"  {'total':28s} {sum(t[:len(names)]) / max(n,1):9.1f} cycles/tile")
@@ -30,7 +29,3 @@ if ver == "5" and t[15]:
     for nm, c in zip(names, t[8:15]):
         print(f"  {nm:28s} {c / max(t[15],1):9.1f} cycles/tile")
     print(f"  {'total':28s} {sum(t[8:15]) / max(t[15],1):9.1f} cycles/tile")
-if ver == "4" and t[8]:
-    t0 = t[8]
-    print(f"life of S(26) in block 0 (cycles after the timed thread released the S buffer of tile 24): issuer reached s_next=26 at +{t[11]-t0}, saw S_FREE +{t[9]-t0}, "
-          f"saw K_FULL and issued +{t[10]-t0}, S(26) landed +{t[12]-t0}")

@@ -174,10 +174,10 @@ def _rows_sum_property():
 
 
 @gpu
-@pytest.mark.parametrize("version", [5, 4, 0])
+@pytest.mark.parametrize("version", [5, 0])
 def test_attention_alternative_kernels(version):
-    """The non-default self-attention kernels (5 / 4: cluster kernels with two softmax groups feeding one accumulator --
-    cta_group::2 MMAs / TMA multicast --, 0: single-tile kernel) against the same oracle comparisons and the full-size row-sum property -- the latter has thousands of
+    """The non-default self-attention kernels (5: cta_group::2 cluster kernel with two softmax groups feeding one accumulator,
+    0: single-tile kernel) against the same oracle comparisons and the full-size row-sum property -- the latter has thousands of
     lazy-rescale events (scores scaled x2), which is what exercises the shared-running-max protocol of kernel 5."""
     L = _lib()
     L.check(L.lib().ce_debug_attention_kernel(version))
