@@ -21,11 +21,11 @@
 // Barriers that gather BOTH CTAs (operands landed, S consumed, P published) live in the leader; completion of the MMAs is
 // multicast to both CTAs with tcgen05.commit.
 //
-// STATUS: parity-green (tests/test_gpu_ops.py::test_attention_alternative_kernels) but NOT the default: 970-1040 TFLOP/s
-// against 1123 for attention2.cu.  scripts/attn_timing.py (per-warp timestamps of tile DBG_TILE) shows each group waiting
-// ~1000 cycles per tile for P.V(j-2): the peer CTA's "P published" arrivals reach the leader ~1100 cycles after the leader's
-// own, so P.V is issued late although the tensor pipe is only 50 % busy -- the per-tile cross-CTA handshakes are in the
-// loop and two S / two P buffers are all the TMEM has to hide them.  Selected with CE_ATTN_V2=5 or
+// STATUS: parity-green (tests/test_gpu_ops.py::test_attention_alternative_kernels) but NOT the default: 1020-1045 TFLOP/s
+// against 1123 for attention2.cu.  scripts/attn_timing.py: leader and peer show identical phase times and uncontended exp
+// phases, but the two handshake loops that cross the CTA pair ("S consumed" -> S(j+2) issued -> "S ready"; "P published" ->
+// P.V issued -> "P.V done") each take ~2000-2300 cycles and two S / two P buffers are all the TMEM has to hide them, so the
+// period stays ~3650 cycles per two tiles wherever the waits are placed.  Selected with CE_ATTN_V2=5 or
 // ce_debug_attention_kernel(5).
 //
 // Replaces F.scaled_dot_product_attention of the self-attention (transformer_chronoedit.py:97-99).
