@@ -1,8 +1,6 @@
 // HBM-bound row kernels of the DiT path: fp32 LayerNorm + adaLN modulate, RMSNorm-across-heads + 3D RoPE,
 // patchify / unpatchify, and the tiny-M Linear layers of the time embedder.  All are coalesced 16-byte
 // accesses with one CTA per token row (rows >> SM count), statistics in fp32 via warp shuffles.
-#include <cstdlib>
-
 #include "elementwise.cuh"
 
 namespace ce {
@@ -10,7 +8,6 @@ namespace ce {
 namespace {
 
 constexpr int ROW_THREADS = 256;
-constexpr int ROWS_PER_CTA = ROW_THREADS / 64;   // one warp pair per row
 constexpr int MAX_D = 8192;                // 64 lanes x 16 vectors x 8 bf16
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -35,14 +32,18 @@ __device__ __forceinline__ float2 pair_sum(float a, float b, float2* part) {
   return make_float2(a + o.x, b + o.y);
 }
 
-// One row by one warp pair.  `xr` = the row's data (global memory, or the shared-memory copy the streaming kernel staged).
 template <int HV>
-__device__ __forceinline__ void layernorm_row(const uint4* __restrict__ xr, float pivot, int row, bool live, bf16* __restrict__ y, int ldy, int D,
-                                              float eps, const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride,
-                                              int rows_per_batch, const float* __restrict__ weight, const float* __restrict__ bias,
-                                              int scale_is_1p, float2* part) {
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
+                 const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
+                 const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
+  __shared__ float2 part[ROW_THREADS / 32];
   const int lane64 = threadIdx.x & 63;
+  int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;  // keep the pair barrier balanced; results are not stored
   const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
   uint4 v[HV];
 #pragma unroll
   for (int i = 0; i < HV; ++i) {
@@ -50,6 +51,7 @@ __device__ __forceinline__ void layernorm_row(const uint4* __restrict__ xr, floa
     v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
   }
   // single statistics pass on pivot-shifted data d = x - x[row, 0]:  mean = pivot + E[d],  var = E[d^2] - E[d]^2
+  const float pivot = __bfloat162float(x[(size_t)row * ldx]);
   float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int i = 0; i < HV; ++i) {
@@ -114,98 +116,24 @@ __device__ __forceinline__ void layernorm_row(const uint4* __restrict__ xr, floa
   }
 }
 
-
-template <int HV>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
-layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
-                 const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
-                 const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
-  __shared__ float2 part[ROW_THREADS / 32];
-  int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 6);
-  const bool live = row < rows;
-  if (!live) row = rows - 1;  // keep the pair barrier balanced; results are not stored
-  const bf16* xrow = x + (size_t)row * ldx;
-  layernorm_row<HV>(reinterpret_cast<const uint4*>(xrow), __bfloat162float(xrow[0]), row, live, y, ldy, D, eps, scale, shift, mod_stride,
-                    rows_per_batch, weight, bias, scale_is_1p, part);
-}
-
-// Streaming form of the row kernels (used at the 14B width): persistent CTAs, each iteration = ROWS_PER_CTA rows staged in
-// shared memory by cp.async.bulk, double buffered, so the next rows are in flight while this iteration's are normalised and
-// stored.  The direct kernels issue all loads of a row, wait, compute, store: the bytes in flight collapse during the
-// arithmetic and the stores (3.3-3.9 TB/s at 14400 x 5120); here the copy engine keeps 40-80 KB per CTA in flight all the time.
-struct RowStream {
-  uint8_t* stage;        // 2 x ROWS_PER_CTA x row_bytes
-  uint64_t* full;        // 2 barriers
-  uint32_t row_bytes;
-  int ngroups, rows;
-  __device__ __forceinline__ void init(uint8_t* dyn, uint64_t* bars, int D, int rows_) {
-    stage = dyn;
-    full = bars;
-    row_bytes = (uint32_t)D * 2u;
-    rows = rows_;
-    ngroups = (rows_ + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-    if (threadIdx.x == 0) {
-      mbar_init(&full[0], 1);
-      mbar_init(&full[1], 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-  }
-  __device__ __forceinline__ void issue(const bf16* x, int ldx, int g, int st) {   // one thread
-    const int r0 = g * ROWS_PER_CTA;
-    const int n = min(ROWS_PER_CTA, rows - r0);
-    fence_proxy_async_smem();   // the stage was read through the generic proxy in the previous iteration
-    mbar_arrive_expect_tx(&full[st], (uint32_t)n * row_bytes);
-    for (int r = 0; r < n; ++r)
-      bulk_load_1d(stage + ((size_t)st * ROWS_PER_CTA + r) * row_bytes, x + (size_t)(r0 + r) * ldx, row_bytes, &full[st]);
-  }
-  __device__ __forceinline__ const uint8_t* row_ptr(int st, int g) const {   // this warp pair's row (clamped for a ragged last group)
-    const int n = min(ROWS_PER_CTA, rows - g * ROWS_PER_CTA);
-    const int r = min((int)(threadIdx.x >> 6), n - 1);
-    return stage + ((size_t)st * ROWS_PER_CTA + r) * row_bytes;
-  }
-};
-
-template <int HV>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
-layernorm_stream_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
-                        const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
-                        const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p) {
-  extern __shared__ __align__(128) uint8_t row_stage[];
-  __shared__ float2 part[ROW_THREADS / 32];
-  __shared__ __align__(8) uint64_t full[2];
-  RowStream rs;
-  rs.init(row_stage, full, D, rows);
-  int g = blockIdx.x;
-  if (threadIdx.x == 0 && g < rs.ngroups) rs.issue(x, ldx, g, 0);
-  for (int it = 0; g < rs.ngroups; g += gridDim.x, ++it) {
-    const int st = it & 1;
-    if (threadIdx.x == 0 && g + (int)gridDim.x < rs.ngroups) rs.issue(x, ldx, g + gridDim.x, st ^ 1);
-    mbar_wait(&full[st], (it >> 1) & 1, 900);
-    int row = g * ROWS_PER_CTA + (threadIdx.x >> 6);
-    const bool live = row < rows;
-    if (!live) row = rows - 1;
-    const uint8_t* src = rs.row_ptr(st, g);
-    layernorm_row<HV>(reinterpret_cast<const uint4*>(src), __bfloat162float(*reinterpret_cast<const bf16*>(src)), row, live, y, ldy, D, eps, scale,
-                      shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p, part);
-    __syncthreads();   // stage st and `part` are free again
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// One row by one warp pair: `src` = the row's data (global, or the staged shared-memory copy), `xr` = where the result goes.
 template <int HV>
-__device__ __forceinline__ void rmsnorm_rope_row(const uint4* __restrict__ src, uint4* __restrict__ xr, int row, bool live, int D, float eps,
-                                                 const bf16* __restrict__ weight, const float* __restrict__ rope_cos,
-                                                 const float* __restrict__ rope_sin, int L, int head_dim, float2* part) {
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
+                    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
+  __shared__ float2 part[ROW_THREADS / 32];
   const int lane64 = threadIdx.x & 63;
+  int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
   const int nvec = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
   uint4 v[HV];
 #pragma unroll
   for (int i = 0; i < HV; ++i) {
     const int idx = lane64 + i * 64;
-    v[i] = idx < nvec ? src[idx] : make_uint4(0u, 0u, 0u, 0u);
+    v[i] = idx < nvec ? xr[idx] : make_uint4(0u, 0u, 0u, 0u);
   }
   float ss = 0.f;
 #pragma unroll
@@ -245,43 +173,6 @@ __device__ __forceinline__ void rmsnorm_rope_row(const uint4* __restrict__ src, 
       }
       if (live) xr[idx] = pack8(o);
     }
-  }
-}
-
-
-template <int HV>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
-rmsnorm_rope_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
-                    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
-  __shared__ float2 part[ROW_THREADS / 32];
-  int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 6);
-  const bool live = row < rows;
-  if (!live) row = rows - 1;
-  uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
-  rmsnorm_rope_row<HV>(xr, xr, row, live, D, eps, weight, rope_cos, rope_sin, L, head_dim, part);
-}
-
-template <int HV>
-__global__ void __launch_bounds__(ROW_THREADS, 2)
-rmsnorm_rope_stream_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight,
-                           const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L, int head_dim) {
-  extern __shared__ __align__(128) uint8_t row_stage[];
-  __shared__ float2 part[ROW_THREADS / 32];
-  __shared__ __align__(8) uint64_t full[2];
-  RowStream rs;
-  rs.init(row_stage, full, D, rows);
-  int g = blockIdx.x;
-  if (threadIdx.x == 0 && g < rs.ngroups) rs.issue(x, ldx, g, 0);
-  for (int it = 0; g < rs.ngroups; g += gridDim.x, ++it) {
-    const int st = it & 1;
-    if (threadIdx.x == 0 && g + (int)gridDim.x < rs.ngroups) rs.issue(x, ldx, g + gridDim.x, st ^ 1);
-    mbar_wait(&full[st], (it >> 1) & 1, 901);
-    int row = g * ROWS_PER_CTA + (threadIdx.x >> 6);
-    const bool live = row < rows;
-    if (!live) row = rows - 1;
-    rmsnorm_rope_row<HV>(reinterpret_cast<const uint4*>(rs.row_ptr(st, g)), reinterpret_cast<uint4*>(x + (size_t)row * ldx), row, live, D, eps, weight,
-                         rope_cos, rope_sin, L, head_dim, part);
-    __syncthreads();   // stage st and `part` are free again
   }
 }
 
@@ -397,15 +288,6 @@ __global__ void add_table_kernel(const float* __restrict__ table, int table_rows
 
 }  // namespace
 
-// The streaming kernels pay off when there are several row groups per resident CTA; CE_ROW_STREAM=0 forces the direct kernels (A/B).
-static bool use_row_stream(int rows, int D) {
-  static const bool on = [] {
-    const char* e = getenv("CE_ROW_STREAM");
-    return !(e && e[0] == '0');
-  }();
-  return on && D % 8 == 0 && rows >= 8 * ROWS_PER_CTA * device_sm_count();
-}
-
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale,
                      const float* shift, int mod_stride, int rows_per_batch, const float* weight, const float* bias,
                      cudaStream_t stream, int scale_is_1p) {
@@ -419,20 +301,8 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, 
 #define CE_LN(V) layernorm_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p)
   if (nvec <= 128) CE_LN(2);
   else if (nvec <= 256) CE_LN(4);
-  else if (nvec <= 640) {
-    if (use_row_stream(rows, D)) {   // the 14B width: persistent CTAs, rows staged by the copy engine (see RowStream)
-      const size_t smem = 2 * (size_t)ROWS_PER_CTA * D * 2;
-      static bool attr_set = false;
-      if (!attr_set) {
-        CE_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ROWS_PER_CTA * 640 * 8 * 2)));
-        attr_set = true;
-      }
-      const int sgrid = grid < 2 * device_sm_count() ? grid : 2 * device_sm_count();
-      layernorm_stream_kernel<10><<<sgrid, ROW_THREADS, smem, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p);
-    } else {
-      CE_LN(10);
-    }
-  } else CE_LN(16);
+  else if (nvec <= 640) CE_LN(10);
+  else CE_LN(16);
 #undef CE_LN
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
@@ -448,20 +318,8 @@ int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16
 #define CE_RMS(V) rmsnorm_rope_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim)
   if (nvec <= 128) CE_RMS(2);
   else if (nvec <= 256) CE_RMS(4);
-  else if (nvec <= 640) {
-    if (use_row_stream(rows, D)) {
-      const size_t smem = 2 * (size_t)ROWS_PER_CTA * D * 2;
-      static bool attr_set = false;
-      if (!attr_set) {
-        CE_CHECK_CUDA(cudaFuncSetAttribute(rmsnorm_rope_stream_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ROWS_PER_CTA * 640 * 8 * 2)));
-        attr_set = true;
-      }
-      const int sgrid = grid < 2 * device_sm_count() ? grid : 2 * device_sm_count();
-      rmsnorm_rope_stream_kernel<10><<<sgrid, ROW_THREADS, smem, stream>>>(x, ldx, rows, D, eps, weight, rope_cos, rope_sin, L, head_dim);
-    } else {
-      CE_RMS(10);
-    }
-  } else CE_RMS(16);
+  else if (nvec <= 640) CE_RMS(10);
+  else CE_RMS(16);
 #undef CE_RMS
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;

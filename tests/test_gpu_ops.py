@@ -191,7 +191,7 @@ def test_attention_alternative_kernels(version):
 
 @gpu
 @pytest.mark.parametrize("rows,D,mode", [(300, 256, "mod"), (77, 5120, "mod"), (64, 1280, "affine"), (33, 384, "plain"),
-                                         (4739, 5120, "mod"), (4736, 3072, "affine"), (5003, 5120, "plain")])   # >= 4736 rows: streaming kernels, ragged tails
+                                         (4739, 5120, "mod"), (4736, 3072, "affine"), (5003, 5120, "plain")])   # large row counts with ragged tails
 def test_layernorm(rows, D, mode):
     L = _lib()
     lib = L.lib()
@@ -220,7 +220,7 @@ def test_layernorm(rows, D, mode):
 
 
 @gpu
-@pytest.mark.parametrize("rows,H,rope", [(234, 3, True), (126, 2, False), (600, 40, True), (4746, 40, True), (4740, 24, False)])   # last two: streaming kernel
+@pytest.mark.parametrize("rows,H,rope", [(234, 3, True), (126, 2, False), (600, 40, True), (4746, 40, True), (4740, 24, False)])   # last two: large, ragged
 def test_rmsnorm_rope(rows, H, rope):
     from oracle import dit_oracle as O
 
