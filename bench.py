@@ -179,6 +179,24 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------
+# Algorithmic work, restated here so that the measured arm does not touch oracle/ at all:
+# 2*MAC for every Linear, 4*Lq*Lk*D for every attention; tests/test_oracle.py checks these against the oracle's own counters.
+def dit_flops_per_forward(layers: int, frames: int, lat_h: int, lat_w: int, text_len: int, image_len: int, batch: int) -> float:
+    D, Fd, cin, cout, text_dim, image_dim, freq_dim = 5120, 13824, 36, 16, 4096, 1280, 256
+    L = frames * (lat_h // 2) * (lat_w // 2)
+    per_block = (2 * L * D * 3 * D + 4 * L * L * D + 2 * L * D * D            # self: q,k,v / SDPA / out
+                 + 2 * L * D * D + 2 * text_len * D * 2 * D + 2 * image_len * D * 2 * D   # cross: q / text k,v / image k,v
+                 + 4 * L * (text_len + image_len) * D + 2 * L * D * D          # cross: SDPA / out
+                 + 2 * 2 * L * D * Fd)                                          # ffn
+    embed = (2 * L * cin * 4 * D + 2 * L * D * cout * 4 + 2 * text_len * (text_dim * D + D * D)
+             + 2 * image_len * (image_dim ** 2 + image_dim * D) + 2 * (freq_dim * D + D * D + D * 6 * D))
+    return float(batch) * (layers * per_block + embed)
+
+
+VAE_ENCODE_FLOP = 24577494220800.0   # conv FLOPs of one 5 x 720 x 1280 encode / decode (24.58 / 41.04 TFLOP)
+VAE_DECODE_FLOP = 41036724633600.0
+
+
 def init_weights_(model, seed: int):
     """Random-init weights of the 14B architecture directly on the device (there is no checkpoint on the box):
     Linear ~ N(0, 0.02), norms ~ 1 + 0.1 N, scale_shift_table ~ N(0,1)/sqrt(D) (as transformer_chronoedit.py:265, 393)."""
@@ -205,7 +223,6 @@ def run_ours(args):
 
     import chronoedit_b200 as ce
     from chronoedit_b200 import _lib
-    from oracle import dit_oracle as O
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -333,8 +350,6 @@ def run_ours(args):
     # the VAE bookends of one edit (encode of the condition video, decode of the result), timed once per run
     edit = None
     if not args.no_vae:
-        from oracle import vae_oracle as V
-
         vae = ce.AutoencoderKLWan(device=dev)
         gv = torch.Generator(device=dev).manual_seed(7)
         for n, p in vae.named_parameters():
@@ -364,12 +379,11 @@ def run_ours(args):
         enc_launches = vae.launches()
         dec_ms = time_once(lambda: vae.decode(zlat))
         dec_launches = vae.launches()
-        cfgv = V.VAEConfig.wan21()
         step_ms = dev_ms / args.steps
         edit = {
             "vae_encode_ms": enc_ms, "vae_decode_ms": dec_ms, "vae_encode_launches": enc_launches, "vae_decode_launches": dec_launches,
-            "vae_encode_conv_tflops": V.conv_flops(cfgv, 5, 8 * LAT_H, 8 * LAT_W, False) / enc_ms / 1e9,
-            "vae_decode_conv_tflops": V.conv_flops(cfgv, 5, 8 * LAT_H, 8 * LAT_W, True) / dec_ms / 1e9,
+            "vae_encode_conv_tflops": VAE_ENCODE_FLOP / enc_ms / 1e9,
+            "vae_decode_conv_tflops": VAE_DECODE_FLOP / dec_ms / 1e9,
             "vae_decode_algorithmic_GBps": 23.64e9 / dec_ms / 1e6,
             "edits_per_sec_50_steps_all_gpus": world / ((enc_ms + dec_ms + 50 * step_ms) / 1000.0),
             "edits_per_sec_8_steps_no_cfg_all_gpus": world / ((enc_ms + dec_ms + 8 * step_ms / 2) / 1000.0),
@@ -380,7 +394,7 @@ def run_ours(args):
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
-        flops_fwd = O.flops_per_forward(O.DiTConfig(num_layers=args.layers), FRAMES, LAT_H, LAT_W, TEXT_LEN, 257, batch=2)
+        flops_fwd = dit_flops_per_forward(args.layers, FRAMES, LAT_H, LAT_W, TEXT_LEN, 257, batch=2)
         gemm_tf = prof["work"][0] / (prof["ms"][0] / 1000.0) / 1e12 if prof["ms"][0] > 0 else 0.0
         attn_tf = prof["work"][1] / (prof["ms"][1] / 1000.0) / 1e12 if prof["ms"][1] > 0 else 0.0
         kernel_ms = sum(prof["ms"])

@@ -101,3 +101,19 @@ def test_oracle_matches_live_reference():
         y = m(x, t, text, img, return_dict=False)[0]
         o = dit_oracle.dit_forward(sd, case.cfg, x, t, text, img)
     torch.testing.assert_close(o, y, rtol=0, atol=1e-6)
+
+
+def test_bench_flop_counters_match_oracle():
+    """bench.py restates the algorithmic FLOP counts (so its measured arm never imports oracle/); they must equal the oracle's."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_for_test", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    for layers, frames, batch in [(40, 2, 2), (1, 8, 1), (0, 2, 1)]:
+        assert b.dit_flops_per_forward(layers, frames, 90, 160, 512, 257, batch) == dit_oracle.flops_per_forward(
+            dit_oracle.DiTConfig(num_layers=layers), frames, 90, 160, 512, 257, batch=batch)
+    cfg = vae_oracle.VAEConfig.wan21()
+    assert b.VAE_ENCODE_FLOP == vae_oracle.conv_flops(cfg, 5, 720, 1280, False)
+    assert b.VAE_DECODE_FLOP == vae_oracle.conv_flops(cfg, 5, 720, 1280, True)
