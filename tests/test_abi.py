@@ -49,6 +49,15 @@ def test_no_cpu_fallback():
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
     rc = lib.ce_linear_bf16(L.ptr(a), 8, L.ptr(a), 8, None, L.ptr(a), 8, None, 8, 8, 8, 0, None, 0, None, 0, 1, None)
     assert rc != 0
+    # the sampler entry point: argument validation first, then the device check -- never a CPU evaluation
+    args = L.UniPCStepArgsC()
+    x = torch.zeros(64)
+    args.sample_dtype, args.model_dtype, args.n, args.p_order = 0, 0, 64, 1
+    args.cond = args.sample = args.x0_out = args.prev_sample_out = x.data_ptr()
+    assert lib.ce_unipc_step(ctypes.byref(args), None) == -3 and b"no CPU fallback" in lib.ce_last_error()
+    args.p_order = 3
+    assert lib.ce_unipc_step(ctypes.byref(args), None) == -1
+    assert lib.ce_debug_attention_kernel(7) == -1
 
 
 def test_rope_table_host_matches_oracle():
