@@ -28,7 +28,7 @@ struct GemmArgs {
   const float* gate = nullptr;  // [batches, gate_stride] fp32, row -> batch = row / rows_per_batch
   int gate_stride = 0;
   int rows_per_batch = 1;
-  int group_m = 16;             // tile rasterisation: M-tiles per group (L2 reuse)
+  int group_m = 0;              // tile rasterisation: M-tiles per group (L2 reuse); 0 = chosen by launch_gemm_bf16
 };
 
 // out[M,N] = epilogue(A[M,K] (row-major, lda) x W[N,K]^T (row-major = nn.Linear weight, ldw)).
