@@ -278,18 +278,12 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
   if (g.epi == EPI_BIAS_GATE_RESID)
     CE_REQUIRE(g.gate != nullptr && g.gate_stride % 4 == 0 && g.rows_per_batch > 0, "gemm: gate epilogue needs gate");
   GemmArgs a = g;
-  const int bn_pre = a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64);
-  const bool pair_pre = bn_pre == 256 && a.M >= 512 && use_2cta();
-  if (a.group_m <= 0) {
-    // Tiles are rasterised in groups of group_m M-tiles x all N-tiles: the A panel of a group (group_m x tile rows x K) should
-    // stay in L2 while the W panels stream past it.  Measured at the 14B shapes (CE_GEMM_GROUP_M sweep, 4/8/16/29/57): 16 is
-    // best for K = 5120, 8 for K = 13824 (+2 %) and for short M (29 M-tiles: +9 %), one group for everything is -16 %.
-    const int tile_rows = pair_pre ? 2 * BM : BM;
-    const int tiles_m = (a.M + tile_rows - 1) / tile_rows;
-    a.group_m = ((size_t)16 * tile_rows * a.K * 2 > ((size_t)64 << 20) || tiles_m <= 32) ? 8 : 16;
-  }
+  // Tiles are rasterised in groups of group_m M-tiles x all N-tiles so that the A panel of a group stays in L2 while the W
+  // panels stream past it.  Measured at the 14B shapes (CE_GEMM_GROUP_M sweep, repeated A/B): 16 beats 8 by 2 % at K = 5120,
+  // no significant difference at K = 13824 or for 29 M-tiles, 4 is -3..6 %, a single group (57) -16 %.
+  if (a.group_m <= 0) a.group_m = 16;
   {
-    static const int env_gm = [] {   // developer knob (A/B): override the choice above
+    static const int env_gm = [] {   // developer knob (A/B)
       const char* e = getenv("CE_GEMM_GROUP_M");
       return e ? atoi(e) : 0;
     }();
