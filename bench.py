@@ -403,8 +403,11 @@ def run_ours(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": "configs[1]: ChronoEdit-14B single edit, 720x1280, 5 px frames -> latent [1,36,2,90,160] (7200 tokens), "
-                            "512 text + 257 image tokens, CFG 5.0 (2 forwards/step as one batch-2 call), per-GPU independent edits",
+                "workload": ("configs[1]: ChronoEdit-14B single edit, 720x1280, 5 px frames -> latent [1,36,2,90,160] (7200 tokens), "
+                             "512 text + 257 image tokens, CFG 5.0 (2 forwards/step as one batch-2 call), per-GPU independent edits")
+                if FRAMES == 2 else
+                ("DEV (not the headline workload): configs[2] temporal-reasoning geometry, 29 px frames -> latent [1,36,8,90,160] "
+                 "(28800 tokens), CFG 5.0"),
                 "layers": args.layers, "global_batch_edits": world, "parallelism": f"dp{world}",
                 "l2": "inputs larger than L2 (32.8 GB of weights stream every forward); no explicit flush",
                 "latent_update": "value: fused CFG + FlowUniPC step + next model input in one launch (ce_unipc_step); e2e: host-side Euler glue around ce_dit_forward_host",
@@ -449,7 +452,12 @@ def main():
     ap.add_argument("--layers", type=int, default=40, help="DEV ONLY: fewer layers make the number invalid as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the (untimed-region) VAE encode/decode measurement")
+    ap.add_argument("--latent-frames", type=int, default=2, choices=[2, 8],
+                    help="DEV ONLY: 8 = the temporal-reasoning geometry of configs[2] (28 800 tokens); not the headline workload")
     args = ap.parse_args()
+    if args.latent_frames != 2:
+        global FRAMES
+        FRAMES = args.latent_frames
     if args.impl == "reference":
         run_reference_arm(args)
     else:
