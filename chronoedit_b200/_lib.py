@@ -57,6 +57,10 @@ SIGNATURES = {
     "ce_dit_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "ce_dit_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "ce_dit_context_cache_bytes": (c_int64, [c_void_p, c_int, c_int]),
+    "ce_dit_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "ce_dit_set_capture": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "ce_dit_host_staging_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "ce_dit_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

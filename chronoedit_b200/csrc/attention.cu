@@ -456,12 +456,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     tk2 = tk;
     tv2 = tv;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SmemLayout::total));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM(attention_fwd_kernel, SmemLayout::total);
   dim3 grid((a.Lq + BQ - 1) / BQ, a.H, a.B);
   attention_fwd_kernel<<<grid, ATTN_THREADS, SmemLayout::total, stream>>>(tq, tk, tv, tk2, tv2, a);
   CE_CHECK_CUDA(cudaGetLastError());

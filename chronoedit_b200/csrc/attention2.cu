@@ -376,14 +376,10 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
     const int v = e ? atoi(e) : 0;
     return v < 0 ? 0 : (v > 3 ? 3 : v);
   }();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2::total));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM(attention2_fwd_kernel<0>, Smem2::total);
+  CE_ENSURE_SMEM(attention2_fwd_kernel<1>, Smem2::total);
+  CE_ENSURE_SMEM(attention2_fwd_kernel<2>, Smem2::total);
+  CE_ENSURE_SMEM(attention2_fwd_kernel<3>, Smem2::total);
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   switch (poly) {
     case 0: attention2_fwd_kernel<0><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;

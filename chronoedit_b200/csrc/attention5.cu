@@ -399,11 +399,7 @@ int launch_attention5(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap5(&tq, a.q, a.B, a.Lq, a.H, a.ldq, 128))) return rc;
   if ((rc = make_qkv_tmap5(&tk, a.k, a.B, a.Lk, a.H, a.ldk, 64))) return rc;
   if ((rc = make_qkv_tmap5(&tv, a.v, a.B, a.Lk, a.H, a.ldv, 128))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(attention5_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem5::total));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM(attention5_fwd_kernel, Smem5::total);
   const int q_tiles = (a.Lq + BQ - 1) / BQ;
   dim3 grid(2 * ((q_tiles + 1) / 2), a.H, a.B);   // whole clusters: an odd tile count gets one padding CTA
   attention5_fwd_kernel<<<grid, ATTN5_THREADS, Smem5::total, stream>>>(tq, tk, tv, a);

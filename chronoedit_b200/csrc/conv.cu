@@ -222,11 +222,7 @@ conv3d_cl_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
 template <int BN, int STAGES>
 int launch_conv_variant(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, ConvGeom g, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_cl_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM((conv3d_cl_kernel<BN, STAGES>), smem);
   g.tiles_n = (a.Cout + BN - 1) / BN;
   g.num_tiles = a.Tout * g.tiles_h * g.tiles_w * g.tiles_n;
   const int grid = g.num_tiles < device_sm_count() ? g.num_tiles : device_sm_count();

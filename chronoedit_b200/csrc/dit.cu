@@ -34,10 +34,12 @@ struct ce_dit {
   ce_dit_config cfg;
   std::map<std::string, WeightRef> w;
   // RoPE tables, cached per latent geometry
-  int rope_f = 0, rope_h = 0, rope_w = 0;
+  int rope_f = 0, rope_h = 0, rope_w = 0, rope_dev = -1;
   float* rope_cos = nullptr;
   float* rope_sin = nullptr;
   int64_t launches = 0;
+  // parity aid: output of selected blocks copied out (ce_dit_set_capture)
+  std::vector<std::pair<int, void*>> capture;
   // optional per-category device timing (CUDA events on the launch stream around every kernel)
   bool profiling = false;
   std::vector<cudaEvent_t> ev;       // pairs (begin, end)
@@ -227,14 +229,16 @@ int rope_table_host(int hd, int frames, int hp, int wp, int max_seq_len, int ski
 }
 
 int ensure_rope(ce_dit* h, int frames, int hp, int wp, cudaStream_t stream) {
-  if (h->rope_cos && h->rope_f == frames && h->rope_h == hp && h->rope_w == wp) return CE_OK;
+  int dev = 0;
+  CE_CHECK_CUDA(cudaGetDevice(&dev));
+  if (h->rope_cos && h->rope_dev == dev && h->rope_f == frames && h->rope_h == hp && h->rope_w == wp) return CE_OK;
   std::vector<float> cs, sn;
   int rc = rope_table_host(h->cfg.attention_head_dim, frames, hp, wp, h->cfg.rope_max_seq_len, h->cfg.rope_temporal_skip_len,
                            10000.0, cs, sn);
   if (rc) return rc;
-  if (h->rope_cos) {
+  if (h->rope_cos) {  // other geometry, or the handle moved to another device (model.to(...)): rebuild there
     CE_CHECK_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(h->rope_cos);
+    cudaFree(h->rope_cos);  // cudaFree accepts pointers of any device
     cudaFree(h->rope_sin);
     h->rope_cos = h->rope_sin = nullptr;
   }
@@ -243,6 +247,7 @@ int ensure_rope(ce_dit* h, int frames, int hp, int wp, cudaStream_t stream) {
   CE_CHECK_CUDA(cudaMemcpyAsync(h->rope_cos, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
   CE_CHECK_CUDA(cudaMemcpyAsync(h->rope_sin, sn.data(), sn.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
   CE_CHECK_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
+  h->rope_dev = dev;
   h->rope_f = frames;
   h->rope_h = hp;
   h->rope_w = wp;
@@ -364,6 +369,23 @@ int64_t ce_dit_workspace_bytes(const ce_dit* h, int batch, int frames, int heigh
 
 int64_t ce_dit_last_launch_count(const ce_dit* h) { return h ? h->launches : 0; }
 
+int64_t ce_dit_context_cache_bytes(const ce_dit* h, int batch, int text_len) {
+  if (!h || batch < 1 || text_len < 1) return -1;
+  const int64_t D = D_of(h->cfg);
+  const int64_t per_layer = (int64_t)batch * (text_len + (h->cfg.image_dim > 0 ? 257 : 0)) * 2 * D * (int64_t)sizeof(bf16);
+  return ((per_layer + 255) & ~int64_t(255)) * h->cfg.num_layers;
+}
+
+int ce_dit_set_capture(ce_dit* h, const int32_t* layers, void* const* dst, int n) {
+  CE_REQUIRE(h && n >= 0 && (n == 0 || (layers && dst)), "ce_dit_set_capture: arguments");
+  h->capture.clear();
+  for (int i = 0; i < n; ++i) {
+    CE_REQUIRE(layers[i] >= 0 && layers[i] < h->cfg.num_layers && dst[i], "ce_dit_set_capture: layer index / null destination");
+    h->capture.push_back({layers[i], dst[i]});
+  }
+  return CE_OK;
+}
+
 int ce_dit_profile_begin(ce_dit* h, int max_launches) {
   CE_REQUIRE(h && max_launches > 0, "ce_dit_profile_begin: arguments");
   while ((int)h->ev.size() < 2 * max_launches) {
@@ -403,7 +425,16 @@ int ce_dit_profile_end(ce_dit* h, double* ms_out, double* work_out, int64_t* cou
 int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, const void* encoder_hidden_states,
                    const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
                    int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* stream_v) {
+  return ce_dit_forward_ex(h, hidden_states, timestep, encoder_hidden_states, encoder_hidden_states_image, sample, batch, frames, height,
+                           width, text_len, workspace, workspace_bytes, block0_out, nullptr, 0, 0, stream_v);
+}
+
+int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timestep, const void* encoder_hidden_states,
+                      const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
+                      int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* ctx_cache,
+                      int64_t ctx_cache_bytes, int ctx_reuse, void* stream_v) {
   CE_REQUIRE(h && hidden_states && timestep && encoder_hidden_states && sample && workspace, "ce_dit_forward: null argument");
+  CE_REQUIRE(ctx_reuse == 0 || ctx_cache != nullptr, "ce_dit_forward_ex: ctx_reuse needs a context cache");
   int rc = check_device();
   if (rc) return rc;
   if ((rc = validate_geometry(h, batch, frames, height, width, text_len))) return rc;
@@ -420,6 +451,17 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     return fail(CE_ERR_WORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes, got " + std::to_string(workspace_bytes));
   CE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   if ((rc = ensure_rope(h, frames, hp, wp, s))) return rc;
+  // step-invariant context (text / image embedders and every block's cross-attention K/V, :52-60, :147-165): kept in the
+  // caller's cache across the steps of one edit when one is given; recomputed into the workspace otherwise
+  const int64_t kv_t_elems = (int64_t)B * Lt * 2 * D, kv_i_elems = c.image_dim > 0 ? (int64_t)B * Li * 2 * D : 0;
+  const int64_t ctx_layer_bytes = ((kv_t_elems + kv_i_elems) * (int64_t)sizeof(bf16) + 255) & ~int64_t(255);
+  if (ctx_cache) {
+    CE_REQUIRE((reinterpret_cast<uintptr_t>(ctx_cache) & 255) == 0, "ce_dit_forward_ex: context cache must be 256-byte aligned");
+    CE_REQUIRE(ctx_cache_bytes >= ctx_layer_bytes * c.num_layers, "ce_dit_forward_ex: context cache too small (ce_dit_context_cache_bytes)");
+  }
+  auto kv_text_of = [&](int layer) { return ctx_cache ? reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(ctx_cache) + layer * ctx_layer_bytes) : ws.kv_text; };
+  auto kv_img_of = [&](int layer) { return ctx_cache ? kv_text_of(layer) + kv_t_elems : ws.kv_img; };
+  const bool ctx_compute = !(ctx_cache && ctx_reuse);
   h->launches = 0;
   const float attn_scale = 1.0f / sqrtf((float)c.attention_head_dim);
   const std::string ce_ = "condition_embedder.";
@@ -439,10 +481,12 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
   RUN(launch_add_table(W_F32("blocks.scale_shift_table"), c.num_layers, ws.tproj, 6 * D, ws.mod, B, D, 6, s, /*scale chunks 1,4 -> 1+scale*/ 0x12u));
   RUN(launch_add_table(W_F32("scale_shift_table"), 1, ws.temb_bf16, D, ws.modf, B, D, 2, s, /*chunk 1 = scale*/ 0x2u));
   // text: Linear -> GELU(tanh) -> Linear
+  if (ctx_compute) {
   RUN2(linear(h, reinterpret_cast<const bf16*>(encoder_hidden_states), c.text_dim, ce_ + "text_embedder.linear_1", B * Lt, D, c.text_dim,
              ws.text1, D, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
   RUN2(linear(h, ws.text1, D, ce_ + "text_embedder.linear_2", B * Lt, D, D, ws.ctx_text, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-  if (c.image_dim > 0) {  // image: FP32LayerNorm -> Linear -> GELU(erf) -> Linear -> FP32LayerNorm (:111-123)
+  }
+  if (ctx_compute && c.image_dim > 0) {  // image: FP32LayerNorm -> Linear -> GELU(erf) -> Linear -> FP32LayerNorm (:111-123)
     const int I = c.image_dim;
     RUN(launch_layernorm(reinterpret_cast<const bf16*>(encoder_hidden_states_image), I, ws.img0, I, B * Li, I, 1e-5f, nullptr, nullptr, 0, 0,
                          W_F32(ce_ + "image_embedder.norm1.weight"), W_F32(ce_ + "image_embedder.norm1.bias"), s));
@@ -477,21 +521,25 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     bf16* q2 = ws.qkv;  // [M, D]
     RUN2(linear(h, ws.xn, D, p + "attn2.to_q", M, D, D, q2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
     RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
-    RUN2(linear(h, ws.ctx_text, D, p + "attn2.to_kv", B * Lt, 2 * D, D, ws.kv_text, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-    RUN(launch_rmsnorm_rope(ws.kv_text, 2 * D, B * Lt, D, c.eps, W_BF16(p + "attn2.norm_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
-    if (c.image_dim > 0) {
-      RUN2(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, ws.kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-      RUN(launch_rmsnorm_rope(ws.kv_img, 2 * D, B * Li, D, c.eps, W_BF16(p + "attn2.norm_added_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+    bf16* kv_text = kv_text_of(i);
+    bf16* kv_img = kv_img_of(i);
+    if (ctx_compute) {
+      RUN2(linear(h, ws.ctx_text, D, p + "attn2.to_kv", B * Lt, 2 * D, D, kv_text, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+      RUN(launch_rmsnorm_rope(kv_text, 2 * D, B * Lt, D, c.eps, W_BF16(p + "attn2.norm_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+      if (c.image_dim > 0) {
+        RUN2(linear(h, ws.ctx_img, D, p + "attn2.add_kv_proj", B * Li, 2 * D, D, kv_img, 2 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+        RUN(launch_rmsnorm_rope(kv_img, 2 * D, B * Li, D, c.eps, W_BF16(p + "attn2.norm_added_k.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+      }
     }
     {  // text and image cross-attention in ONE launch: two key/value sources, two softmaxes, results added (:84-104)
       AttnArgs a;
       a.B = B; a.H = H; a.Lq = L; a.Lk = Lt;
       a.q = q2; a.ldq = D;
-      a.k = ws.kv_text; a.ldk = 2 * D;
-      a.v = ws.kv_text + D; a.ldv = 2 * D;
+      a.k = kv_text; a.ldk = 2 * D;
+      a.v = kv_text + D; a.ldv = 2 * D;
       if (c.image_dim > 0) {
-        a.k2 = ws.kv_img; a.ldk2 = 2 * D;
-        a.v2 = ws.kv_img + D; a.ldv2 = 2 * D;
+        a.k2 = kv_img; a.ldk2 = 2 * D;
+        a.v2 = kv_img + D; a.ldv2 = 2 * D;
         a.Lk2 = Li;
       }
       a.out = ws.attn; a.ldo = D;
@@ -505,6 +553,8 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
     RUN2(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s));
     if (i == 0 && block0_out)
       CE_CHECK_CUDA(cudaMemcpyAsync(block0_out, ws.x, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+    for (const auto& cap : h->capture)
+      if (cap.first == i) CE_CHECK_CUDA(cudaMemcpyAsync(cap.second, ws.x, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
   }
 
   // ---- output head (:451-467): modf = [B, 2, D] with shift = chunk 0, scale = chunk 1

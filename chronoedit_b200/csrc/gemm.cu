@@ -242,12 +242,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 template <int BN, int STAGES>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM((gemm_bf16_kernel<BN, STAGES>), smem);
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, g);

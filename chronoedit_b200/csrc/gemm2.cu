@@ -234,11 +234,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 
 int launch_gemm_bf16_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  CE_ENSURE_SMEM(gemm_bf16_2cta_kernel, smem);
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + BN - 1) / BN);
   int clusters = device_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;

@@ -1,6 +1,8 @@
 #include "host_common.h"
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace ce {
 
@@ -61,14 +63,32 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return make_tmap_bf16(out, base, 2, dims, strides, box);
 }
 
+constexpr int kMaxDevices = 64;
+
 int device_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes already opted in
+  int dev = 0;
+  CE_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return CE_OK;
+  CE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+  return CE_OK;
 }
 
 int check_device() {

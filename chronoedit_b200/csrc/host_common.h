@@ -47,7 +47,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // 2-D row-major [rows, cols] bf16 with leading dimension `ld` (elements); box = [box_rows, 64 cols].
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-int device_sm_count();
-int check_device();  // CE_OK iff the current device is compute capability 10.x
+int device_sm_count();   // of the CURRENT device (cached per device index)
+int check_device();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and a process
+// may drive several GPUs (VAE on cuda:1, DiT on cuda:0; model.to() after a first forward).
+int ensure_dynamic_smem(const void* kernel, int bytes);
+#define CE_ENSURE_SMEM(kernel, bytes)                                                              \
+  do {                                                                                             \
+    int _rc = ::ce::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes));      \
+    if (_rc) return _rc;                                                                           \
+  } while (0)  // CE_OK iff the current device is compute capability 10.x
 
 }  // namespace ce

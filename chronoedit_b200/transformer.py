@@ -147,6 +147,7 @@ class ChronoEditTransformer3DModel(nn.Module):
         *,
         torch_dtype: torch.dtype = torch.bfloat16,
         device: Optional[Union[str, torch.device]] = None,
+        cache_context: bool = False,
     ) -> None:
         super().__init__()
         if torch_dtype != torch.bfloat16:
@@ -177,6 +178,12 @@ class ChronoEditTransformer3DModel(nn.Module):
         self._pack_keepalive: Dict[str, torch.Tensor] = {}
         self._workspaces: Dict[Tuple, torch.Tensor] = {}
         self.last_block0: Optional[torch.Tensor] = None
+        # opt-in hoisting of the step-invariant context (text / image embedders, cross-attention K/V of all blocks): see
+        # `ce_dit_forward_ex` in include/chronoedit_b200.h.  Up to `_ctx_slots` (prompt, negative prompt) entries, LRU.
+        self.cache_context = bool(cache_context)
+        self._ctx_slots = 2
+        self._ctx_cache: list = []   # entries: dict(txt=, img=, txt_v=, img_v=, shape=, buf=)
+        self.last_captures: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------ plumbing
     @property
@@ -190,6 +197,8 @@ class ChronoEditTransformer3DModel(nn.Module):
     def _apply(self, fn, *a, **k):
         # .to()/.cuda()/.cpu() re-allocate parameters: the fused device buffers must be rebuilt
         self._packed = False
+        self._ctx_cache = []
+        self._workspaces = {}
         return super()._apply(fn, *a, **k)
 
     def __del__(self):
@@ -264,6 +273,7 @@ class ChronoEditTransformer3DModel(nn.Module):
         check(L.ce_dit_weights_complete(self._handle))
         self._pack_keepalive = keep
         self._packed = True
+        self._ctx_cache = []   # cached K/V were projected with the previous weights
 
     def _workspace(self, B, T, H, W, Lt) -> torch.Tensor:
         key = (B, T, H, W, Lt, str(self.device))
@@ -288,9 +298,15 @@ class ChronoEditTransformer3DModel(nn.Module):
         return_dict: bool = True,
         attention_kwargs: Optional[Dict[str, Any]] = None,
         return_block0: bool = False,
+        capture_layers: Optional[Tuple[int, ...]] = None,
     ) -> Union[Transformer2DModelOutput, Tuple[torch.Tensor]]:
-        # attention_kwargs["scale"] only matters for un-fused PEFT LoRA layers (transformer_chronoedit.py:406-419);
-        # the CLI fuses LoRA into the weights before inference, so it is accepted and ignored like the non-PEFT branch.
+        # attention_kwargs["scale"] only matters for un-fused PEFT LoRA layers (transformer_chronoedit.py:406-419): without the
+        # PEFT backend the reference warns and ignores it (:416-419); this mirror holds fused weights only, so it does the same.
+        if attention_kwargs is not None and float(attention_kwargs.get("scale", 1.0)) != 1.0:
+            import warnings
+
+            warnings.warn("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective "
+                          "(LoRA must be fused with fuse_lora(lora_scale=...) before inference).")
         if not self._packed:
             self.pack_weights()
         dev = self.device
@@ -319,13 +335,58 @@ class ChronoEditTransformer3DModel(nn.Module):
         if return_block0:
             L_tok = T * (H // 2) * (W // 2)
             b0 = torch.empty(B * L_tok, self.config.num_attention_heads * self.config.attention_head_dim, dtype=torch.bfloat16, device=dev)
-        with torch.cuda.device(dev):
-            check(_lib.lib().ce_dit_forward(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws),
-                                           ws.numel(), ptr(b0), current_stream()))
+        caps: Dict[int, torch.Tensor] = {}
+        if capture_layers:
+            L_tok = T * (H // 2) * (W // 2)
+            Dm = self.config.num_attention_heads * self.config.attention_head_dim
+            caps = {int(l): torch.empty(B * L_tok, Dm, dtype=torch.bfloat16, device=dev) for l in capture_layers}
+            lay = (_lib.c_int32 * len(caps))(*caps.keys())
+            dst = (_lib.c_void_p * len(caps))(*[v.data_ptr() for v in caps.values()])
+            check(_lib.lib().ce_dit_set_capture(self._handle, lay, dst, len(caps)))
+        ctx_buf, ctx_reuse = (None, 0)
+        if self.cache_context:
+            ctx_buf, ctx_reuse = self._context_slot(encoder_hidden_states, encoder_hidden_states_image, txt, img)
+        try:
+            with torch.cuda.device(dev):
+                check(_lib.lib().ce_dit_forward_ex(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws),
+                                                  ws.numel(), ptr(b0), ptr(ctx_buf), ctx_buf.numel() if ctx_buf is not None else 0,
+                                                  ctx_reuse, current_stream()))
+        finally:
+            if caps:
+                check(_lib.lib().ce_dit_set_capture(self._handle, None, None, 0))
         self.last_block0 = b0
+        self.last_captures = caps
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)
+
+    def _context_slot(self, txt_in, img_in, txt, img):
+        """(cache buffer, reuse flag) for these encoder states.  A hit requires the SAME tensor objects the cache entry was
+        filled from (the entry holds references, so their storage cannot have been recycled) at the same in-place version
+        counter -- the unchanged pipeline passes the same `prompt_embeds` / `negative_prompt_embeds` / `image_embeds` objects at
+        every step (pipeline_chronoedit.py:715-735)."""
+        ver = lambda t: None if t is None else t._version
+        for e in self._ctx_cache:
+            if e["txt"] is txt_in and e["img"] is img_in and e["txt_v"] == ver(txt_in) and e["img_v"] == ver(img_in):
+                self._ctx_cache.remove(e)
+                self._ctx_cache.append(e)   # most recently used last
+                return e["buf"], 1
+        B, Lt = txt.shape[0], txt.shape[1]
+        n = _lib.lib().ce_dit_context_cache_bytes(self._handle, B, Lt)
+        if n < 0:
+            check(-1)
+        buf = None
+        if len(self._ctx_cache) >= self._ctx_slots:
+            old = self._ctx_cache.pop(0)
+            if old["buf"].numel() >= n and old["buf"].device == self.device:
+                buf = old["buf"]
+        if buf is None:
+            buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._ctx_cache.append(dict(txt=txt_in, img=img_in, txt_v=ver(txt_in), img_v=ver(img_in), buf=buf))
+        return buf, 0
+
+    def clear_context_cache(self) -> None:
+        self._ctx_cache = []
 
     @torch.no_grad()
     def forward_host(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,

@@ -85,6 +85,22 @@ int ce_dit_forward(ce_dit* h, const void* hidden_states, const float* timestep, 
                    const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
                    int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* stream);
 
+/* The same forward with the STEP-INVARIANT context kept across calls: the text / image embedders (:147-165) and every block's
+ * cross-attention K/V projections + RMSNorm (:52-60, :84-95) depend only on encoder_hidden_states[_image] and the weights, not
+ * on the latents or the timestep, so within one edit they are the same at every denoising step.
+ *   ctx_cache: device buffer of >= ce_dit_context_cache_bytes(h, batch, text_len) bytes owned by the caller, or NULL (= ce_dit_forward);
+ *   ctx_reuse = 0: compute the context and leave it in ctx_cache;  ctx_reuse = 1: the cache already holds the context of THESE
+ *   encoder states and weights (the caller's promise) -- the embedders and the 2 x num_layers K/V GEMMs are skipped.
+ * The result is bit-identical either way (same kernels, same inputs).  Algorithmic FLOP counts in bench.py stay un-hoisted. */
+int64_t ce_dit_context_cache_bytes(const ce_dit* h, int batch, int text_len);
+int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timestep, const void* encoder_hidden_states,
+                      const void* encoder_hidden_states_image, void* sample, int batch, int frames, int height, int width,
+                      int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* ctx_cache,
+                      int64_t ctx_cache_bytes, int ctx_reuse, void* stream);
+
+/* Parity aid: from now on every forward copies the output of block layers[i] ([B*L, D] bf16) to dst[i] (n = 0 clears). */
+int ce_dit_set_capture(ce_dit* h, const int32_t* layers, void* const* dst, int n);
+
 /* Same call with every tensor in (pinned) HOST memory: H2D copies of the inputs, forward, D2H of the sample, all on
  * `stream`, which is synchronised before returning.  `staging` is a device buffer of at least
  * ce_dit_host_staging_bytes(...) bytes.  This is the end-to-end ("e2e") path bench.py times. */

@@ -278,7 +278,7 @@ def block(sd: Dict[str, Tensor], i: int, cfg: DiTConfig, x: Tensor, ctx: Tensor,
 def timestep_sinusoid(timestep: Tensor, dim: int) -> Tensor:
     """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=timestep.device) / half
     emb = timestep[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -318,7 +318,7 @@ def dit_forward(sd: Dict[str, Tensor], cfg: DiTConfig, hidden_states: Tensor, ti
     B, _, T, Hh, Ww = hidden_states.shape
     pt, ph, pw = cfg.patch_size
     ppf, pph, ppw = T // pt, Hh // ph, Ww // pw
-    freqs = rope_table(cfg, T, Hh, Ww)
+    freqs = rope_table(cfg, T, Hh, Ww).to(hidden_states.device)  # the oracle also runs on CUDA tensors (tests at BASELINE sizes)
     x = F.conv3d(hidden_states, sd["patch_embedding.weight"], sd["patch_embedding.bias"], stride=cfg.patch_size)
     x = x.flatten(2).transpose(1, 2)
     temb, tproj, text, image = condition_embedder(sd, cfg, timestep, encoder_hidden_states,

@@ -52,6 +52,35 @@ def bench_attn(B=2, H=40, Lq=7200, Lk=7200, nbuf=3):
     print(json.dumps({"op": "attention", "B": B, "H": H, "Lq": Lq, "Lk": Lk, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
 
 
+def bench_attn_libs(B=2, H=40, L=7200, Lk=None):
+    """The library bar for the self-attention: what the unmodified reference executes on a cc-10.0 GPU --
+    torch SDPA with the cuDNN fused-attention backend (chronoedit/_src/modules/attention.py:129-138 picks it on Blackwell), torch's
+    built-in flash backend, and the flash-attn 2.8 package -- on the same shapes, same timing loop."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    Lk = Lk or L
+    q = torch.randn(B, H, L, 128, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(B, H, Lk, 128, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(B, H, Lk, 128, device="cuda", dtype=torch.bfloat16)
+    fl = 4.0 * B * H * L * Lk * 128
+    for name, backend in (("sdpa_cudnn", SDPBackend.CUDNN_ATTENTION), ("sdpa_flash", SDPBackend.FLASH_ATTENTION),
+                          ("sdpa_efficient", SDPBackend.EFFICIENT_ATTENTION)):
+        try:
+            with sdpa_kernel(backend):
+                ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=5, warmup=2)
+            print(json.dumps({"op": name, "B": B, "H": H, "Lq": L, "Lk": Lk, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"op": name, "Lq": L, "error": str(e)[:160]}), flush=True)
+    try:
+        from flash_attn import flash_attn_func
+
+        qf, kf, vf = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+        ms = timeit(lambda: flash_attn_func(qf, kf, vf), iters=5, warmup=2)
+        print(json.dumps({"op": "flash_attn_2.8_pkg", "B": B, "H": H, "Lq": L, "Lk": Lk, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"op": "flash_attn_2.8_pkg", "error": str(e)[:160]}), flush=True)
+
+
 def bench_attn_dual(B=2, H=40, Lq=7200, Lk=512, Lk2=257):
     """The cross-attention launch of the DiT block: text keys + image keys in one kernel."""
     D = H * 128
@@ -132,6 +161,13 @@ if __name__ == "__main__":
         bench_attn(Lk=512)
         bench_attn(Lk=257)
         bench_attn_dual()
+    if "attnlib" in what:
+        bench_attn()
+        bench_attn_libs()
+        bench_attn(B=1, Lq=28800, Lk=28800, nbuf=2)
+        bench_attn_libs(B=1, L=28800)
+        bench_attn(Lk=512)
+        bench_attn_libs(L=7200, Lk=512)
     if "gemm" in what:
         for (M, N, K, epi) in [(14400, 15360, 5120, 0), (14400, 5120, 5120, 3), (14400, 13824, 5120, 1), (14400, 5120, 13824, 3), (7200, 5120, 5120, 0)]:
             bench_gemm(M, N, K, epi)
