@@ -249,21 +249,14 @@ class AutoencoderKLWan(nn.Module):
     @torch.no_grad()
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         """x [B,3,T,H,W] in [-1,1], T = 1+4k, H and W multiples of 8 -> posterior (mean|logvar [B,2z,1+k,H/8,W/8])."""
-        if not self._is_packed:
-            self.pack_weights()
-        L = _lib.lib()
         if x.dim() != 5 or x.shape[1] != 3:
             raise CEError("encode expects [B, 3, T, H, W]")
         B, _, T, H, W = x.shape
+        if T < 1 or (T - 1) % 4 != 0 or H % 8 != 0 or W % 8 != 0:
+            raise CEError("encode expects T = 1 + 4k frames and H, W multiples of 8")
         x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()
-        n = L.ce_vae_workspace_bytes(self._handle, 0, T, H, W)
-        if n < 0:
-            check(-1)
-        ws = self._workspace(n)
         out = torch.empty(B, 2 * self.z_dim, 1 + (T - 1) // 4, H // 8, W // 8, dtype=torch.bfloat16, device=self.device)
-        with torch.cuda.device(self.device):
-            for b in range(B):
-                check(L.ce_vae_encode(self._handle, ptr(x[b]), ptr(out[b]), T, H, W, ptr(ws), ws.numel(), current_stream()))
+        self._native_encode(x, out)
         post = DiagonalGaussianDistribution(out)
         if not return_dict:
             return (post,)
@@ -272,25 +265,44 @@ class AutoencoderKLWan(nn.Module):
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True):
         """z [B,z_dim,Tl,h,w] -> video [B,3,1+4(Tl-1),8h,8w] (clamped to [-1,1] like diffusers)."""
-        if not self._is_packed:
-            self.pack_weights()
-        L = _lib.lib()
         if z.dim() != 5 or z.shape[1] != self.z_dim:
             raise CEError(f"decode expects [B, {self.z_dim}, T, h, w]")
         B, _, Tl, h, w = z.shape
         z = z.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        out = torch.empty(B, 3, 1 + 4 * (Tl - 1), 8 * h, 8 * w, dtype=torch.bfloat16, device=self.device)
+        self._native_decode(z, out)
+        if not return_dict:
+            return (out,)
+        return DecoderOutput(sample=out)
+
+    # the two places the VAE reaches the C ABI; samples of a batch are independent streams (each has its own causal cache in
+    # the reference too), run back to back on the current stream
+    def _native_encode(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        if not self._is_packed:
+            self.pack_weights()
+        L = _lib.lib()
+        B, _, T, H, W = x.shape
+        n = L.ce_vae_workspace_bytes(self._handle, 0, T, H, W)
+        if n < 0:
+            check(-1)
+        ws = self._workspace(n)
+        with torch.cuda.device(self.device):
+            for b in range(B):
+                check(L.ce_vae_encode(self._handle, ptr(x[b]), ptr(out[b]), T, H, W, ptr(ws), ws.numel(), current_stream()))
+
+    def _native_decode(self, z: torch.Tensor, out: torch.Tensor) -> None:
+        if not self._is_packed:
+            self.pack_weights()
+        L = _lib.lib()
+        B, _, Tl, h, w = z.shape
         n = L.ce_vae_workspace_bytes(self._handle, 1, Tl, h, w)
         if n < 0:
             check(-1)
         ws = self._workspace(n)
-        out = torch.empty(B, 3, 1 + 4 * (Tl - 1), 8 * h, 8 * w, dtype=torch.bfloat16, device=self.device)
         with torch.cuda.device(self.device):
             for b in range(B):
                 check(L.ce_vae_decode(self._handle, ptr(z[b]), ptr(out[b]), Tl, h, w, int(self.clamp_output), ptr(ws), ws.numel(),
                                       current_stream()))
-        if not return_dict:
-            return (out,)
-        return DecoderOutput(sample=out)
 
     def launches(self) -> int:
         return int(_lib.lib().ce_vae_last_launch_count(self._handle)) if self._handle else 0

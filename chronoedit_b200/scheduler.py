@@ -83,6 +83,7 @@ class FlowUniPCMultistepScheduler:
         self.this_order = 1
         self._step_index = None
         self._begin_index = None
+        self._coef_cache = {}
         self.sigma_min = self.sigmas[-1].item()
         self.sigma_max = self.sigmas[0].item()
 
@@ -128,6 +129,7 @@ class FlowUniPCMultistepScheduler:
         self.this_order = 1
         self._step_index = None
         self._begin_index = None
+        self._coef_cache = {}
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):   # :646-656, on the host copy (no device sync)
         ts = self._timesteps_host if schedule_timesteps is None else [int(t) for t in schedule_timesteps.tolist()]
@@ -153,7 +155,26 @@ class FlowUniPCMultistepScheduler:
         e = torch.expm1(hh)
         return (s_t / s_0).item(), ((1 - s_t) * e).item(), ((1 - s_t) * e).item(), h, hh, e, lam_0
 
+    _COEF_FIELDS = ("sigma", "use_corrector", "c_order", "c_inv_rk", "c_rho0", "c_rho1", "c_x", "c_m0", "c_bh", "p_order", "p_x",
+                    "p_m0", "p_bh", "p_inv_rk", "p_zero")
+
     def _fill_coefficients(self, a: "_lib.UniPCStepArgsC", i: int, dtype: torch.dtype):
+        """Scalars of step i.  They depend only on (i, order history, dtype), so they are computed once per schedule and cached:
+        the steady-state step does no host tensor arithmetic, no 2x2 solve and no .item() beyond this lookup.  (The reference
+        builds R, b on the sample's device and solves there, fm_solvers_unipc.py:587-620; here -- as in the oracle that is pinned
+        bit for bit against a CPU run of the reference -- the solve runs on the host in fp32, which can differ from a CUDA solve
+        in the last ulp of rho before it is rounded to the sample dtype.)"""
+        key = (i, self.this_order, i > 0 and self.last_sample is not None, self.lower_order_nums, dtype)
+        hit = self._coef_cache.get(key)
+        if hit is not None:
+            for f, v in zip(self._COEF_FIELDS, hit[0]):
+                setattr(a, f, v)
+            return hit[1]
+        order = self._compute_coefficients(a, i, dtype)
+        self._coef_cache[key] = (tuple(getattr(a, f) for f in self._COEF_FIELDS), order)
+        return order
+
+    def _compute_coefficients(self, a: "_lib.UniPCStepArgsC", i: int, dtype: torch.dtype):
         a.sigma = self.sigmas[i].item()
         use_corrector = i > 0 and self.last_sample is not None   # :701-705 (disable_corrector is empty)
         a.use_corrector = int(use_corrector)
@@ -222,7 +243,8 @@ class FlowUniPCMultistepScheduler:
                 raise ValueError("model_input_out must be a contiguous bf16 CUDA tensor [B, C_total >= C_latent, T, H, W]")
             a.model_input_out = model_input_out.data_ptr()
             a.inner, a.c_lat, a.c_total = sample[0, 0].numel(), sample.shape[1], model_input_out.shape[1]
-        _lib.check(_lib.lib().ce_unipc_step(ctypes.byref(a), _lib.current_stream()))
+        self._native_step(a, dict(cond=cond, uncond=uncond, sample=sample, last_sample=state[0], m_prev=state[1], m_prev2=state[2],
+                                  x0=x0, corrected=corrected if a.use_corrector else None, prev=prev, model_input=model_input_out))
         # state update of step() (:720-749)
         self.model_outputs = self.model_outputs[1:] + [x0]
         self.timestep_list = self.timestep_list[1:] + [timestep]
@@ -232,6 +254,11 @@ class FlowUniPCMultistepScheduler:
             self.lower_order_nums += 1
         self._step_index += 1
         return prev, x0
+
+    def _native_step(self, a: "_lib.UniPCStepArgsC", tensors: dict) -> None:
+        """The one place the scheduler reaches the C ABI.  `a` already holds every pointer and coefficient; `tensors` names the
+        same buffers as torch tensors (kept alive across the launch; also what a test harness needs to stand in for the kernel)."""
+        _lib.check(_lib.lib().ce_unipc_step(ctypes.byref(a), _lib.current_stream()))
 
     def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor, return_dict: bool = True,
              generator=None):

@@ -307,8 +307,6 @@ class ChronoEditTransformer3DModel(nn.Module):
 
             warnings.warn("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective "
                           "(LoRA must be fused with fuse_lora(lora_scale=...) before inference).")
-        if not self._packed:
-            self.pack_weights()
         dev = self.device
         if hidden_states.dim() != 5:
             raise CEError("hidden_states must be [B, C, T, H, W]")
@@ -329,36 +327,44 @@ class ChronoEditTransformer3DModel(nn.Module):
             if img.shape[1] != 257:
                 raise CEError("encoder_hidden_states_image must have 257 tokens (transformer_chronoedit.py:53)")
         Lt = txt.shape[1]
-        ws = self._workspace(B, T, H, W, Lt)
         out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16, device=dev)
-        b0 = None
-        if return_block0:
-            L_tok = T * (H // 2) * (W // 2)
-            b0 = torch.empty(B * L_tok, self.config.num_attention_heads * self.config.attention_head_dim, dtype=torch.bfloat16, device=dev)
+        L_tok = T * (H // 2) * (W // 2)
+        Dm = self.config.num_attention_heads * self.config.attention_head_dim
+        b0 = torch.empty(B * L_tok, Dm, dtype=torch.bfloat16, device=dev) if return_block0 else None
         caps: Dict[int, torch.Tensor] = {}
         if capture_layers:
-            L_tok = T * (H // 2) * (W // 2)
-            Dm = self.config.num_attention_heads * self.config.attention_head_dim
             caps = {int(l): torch.empty(B * L_tok, Dm, dtype=torch.bfloat16, device=dev) for l in capture_layers}
-            lay = (_lib.c_int32 * len(caps))(*caps.keys())
-            dst = (_lib.c_void_p * len(caps))(*[v.data_ptr() for v in caps.values()])
-            check(_lib.lib().ce_dit_set_capture(self._handle, lay, dst, len(caps)))
-        ctx_buf, ctx_reuse = (None, 0)
-        if self.cache_context:
-            ctx_buf, ctx_reuse = self._context_slot(encoder_hidden_states, encoder_hidden_states_image, txt, img)
-        try:
-            with torch.cuda.device(dev):
-                check(_lib.lib().ce_dit_forward_ex(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws),
-                                                  ws.numel(), ptr(b0), ptr(ctx_buf), ctx_buf.numel() if ctx_buf is not None else 0,
-                                                  ctx_reuse, current_stream()))
-        finally:
-            if caps:
-                check(_lib.lib().ce_dit_set_capture(self._handle, None, None, 0))
+        self._native_forward(x, t, txt, img, out, b0, caps, encoder_hidden_states, encoder_hidden_states_image)
         self.last_block0 = b0
         self.last_captures = caps
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)
+
+    def _native_forward(self, x, t, txt, img, out, b0, caps, txt_in, img_in) -> None:
+        """The one place the DiT forward reaches the C ABI (ce_dit_forward_ex).  x [B,C,T,H,W] bf16, t [B] fp32, txt / img bf16,
+        all contiguous on the module's device; `out` (and the optional block captures) are written in place."""
+        if not self._packed:
+            self.pack_weights()
+        B, _, T, H, W = x.shape
+        Lt = txt.shape[1]
+        L = _lib.lib()
+        ws = self._workspace(B, T, H, W, Lt)
+        if caps:
+            lay = (_lib.c_int32 * len(caps))(*caps.keys())
+            dst = (_lib.c_void_p * len(caps))(*[v.data_ptr() for v in caps.values()])
+            check(L.ce_dit_set_capture(self._handle, lay, dst, len(caps)))
+        ctx_buf, ctx_reuse = (None, 0)
+        if self.cache_context:
+            ctx_buf, ctx_reuse = self._context_slot(txt_in, img_in, txt, img)
+        try:
+            with torch.cuda.device(self.device):
+                check(L.ce_dit_forward_ex(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws), ws.numel(),
+                                          ptr(b0), ptr(ctx_buf), ctx_buf.numel() if ctx_buf is not None else 0, ctx_reuse,
+                                          current_stream()))
+        finally:
+            if caps:
+                check(L.ce_dit_set_capture(self._handle, None, None, 0))
 
     def _context_slot(self, txt_in, img_in, txt, img):
         """(cache buffer, reuse flag) for these encoder states.  A hit requires the SAME tensor objects the cache entry was

@@ -1,0 +1,2 @@
+class FlowMatchEulerDiscreteScheduler:   # annotation only (pipeline_chronoedit.py:168)
+    pass

@@ -26,3 +26,18 @@ def deprecate(*args, **kwargs):  # diffusers.utils.deprecate: warns only
 
 def is_scipy_available():
     return False
+
+
+def is_ftfy_available():
+    return False
+
+
+def is_torch_xla_available():
+    return False
+
+
+def replace_example_docstring(example_docstring):
+    def wrap(fn):
+        return fn
+
+    return wrap

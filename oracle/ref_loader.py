@@ -118,3 +118,29 @@ def load_reference_unipc():
     except ImportError:
         sys.path.insert(0, _SHIM)
     return _load_by_path("_ref_fm_solvers_unipc", os.path.join(REFERENCE_ROOT, "chronoedit", "_src", "models", "fm_solvers_unipc.py"))
+
+
+def load_reference_pipeline():
+    """Returns the module object of the UNMODIFIED chronoedit_diffusers/pipeline_chronoedit.py (class ChronoEditPipeline).
+    Its diffusers imports (:25-34) resolve to the shim, `chronoedit_diffusers.transformer_chronoedit` and
+    `chronoedit._ext.imaginaire.utils.log` to the reference tree itself, and the guardrail presets (:36; import chain needs nltk,
+    better_profanity, retinaface ... -- only CALLED when guardrails are enabled) to an empty stub module."""
+    if "_ref_pipeline_chronoedit" in sys.modules:
+        return sys.modules["_ref_pipeline_chronoedit"]
+    try:
+        import diffusers  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, _SHIM)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+    def _blocked(*a, **k):
+        raise RuntimeError("guardrails are stubbed out in the oracle environment; construct the pipeline with disable_guardrails=True")
+
+    for pkg in ("chronoedit._ext.imaginaire.auxiliary", "chronoedit._ext.imaginaire.auxiliary.guardrail",
+                "chronoedit._ext.imaginaire.auxiliary.guardrail.common"):
+        _stub(pkg)
+    presets = _stub("chronoedit._ext.imaginaire.auxiliary.guardrail.common.presets", create_text_guardrail_runner=_blocked,
+                    create_video_guardrail_runner=_blocked, run_text_guardrail=_blocked, run_video_guardrail=_blocked)
+    sys.modules["chronoedit._ext.imaginaire.auxiliary.guardrail.common"].presets = presets
+    return _load_by_path("_ref_pipeline_chronoedit", os.path.join(REFERENCE_ROOT, "chronoedit_diffusers", "pipeline_chronoedit.py"))
