@@ -44,8 +44,13 @@ struct Smem2 {
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV,
        P_FULL = S_FULL + 2 /* [half*2 + q]: keys 0-63 / 64-127 of the tile */, PV_DONE = P_FULL + 4, NUM_BARS2 = PV_DONE + 2 };
 
-// POLY of every 4 exp2 pairs are evaluated on the FMA pipe (f2_exp2_poly), the rest on the MUFU
-template <int POLY>
+// POLY8 of every 8 exp2 pairs are evaluated on the FMA pipe (f2_exp2_poly), the rest on the MUFU.
+// SPEC: from the second key tile on, the exponentials of a tile start against the running maximum of the PREVIOUS tiles as
+// soon as the first 32 score columns have arrived from TMEM, while the other 96 columns are still in flight and the tile's own
+// row maximum is folded in between the MUFU instructions; only when that maximum turns out to exceed the running one by more
+// than the lazy-rescale threshold (rare after the first tiles) is the tile redone the classic way (max first).  Results are
+// bit-identical to the non-speculative order: when no rescale is due the classic path uses the same stale maximum.
+template <int POLY8, bool SPEC>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
@@ -133,6 +138,9 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
         mbar_wait(&bars[Q_FULL], 0, 1);
         int s_next[2] = {0, 0}, pv_next[2] = {0, 0}, pv_half[2] = {0, 0};
+        const bool timed_i = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define CE_EVT(jj, slot)                                                             \
+  if (timed_i && qt == 0 && (jj) >= 16 && (jj) < 24) a.timing[64 + ((jj)-16) * 8 + (slot)] = clock64();
         uint64_t t_start = 0;
         uint32_t idle = 0;
         while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
@@ -157,6 +165,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                                IDESC_S, kk != 0);
                 }
                 umma_commit(&bars[S_FULL + qt]);
+                CE_EVT(j, 5)
                 ++s_next[qt];
                 if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
                 progress = true;
@@ -176,6 +185,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                 for (int kk = 0; kk < BKV / 32; ++kk)
                   umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
                 pv_half[qt] = 1;
+                CE_EVT(j, 3)
                 progress = true;
               }
               if (pv_half[qt] == 1 && mbar_test_wait(&bars[P_FULL + 2 + qt], j & 1)) {
@@ -184,6 +194,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                 for (int kk = BKV / 32; kk < BKV / 16; ++kk)
                   umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, 1);
                 umma_commit(&bars[PV_DONE + qt]);
+                CE_EVT(j, 4)
                 pv_half[qt] = 0;
                 ++pv_next[qt];
                 if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
@@ -232,70 +243,111 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
       CE_TICK(0)
+      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 0] = clock64();
       uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
-      tmem_ld_wait();
-      CE_TICK(1)
-      if (valid < BKV) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
-      }
-      float mx8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
-#pragma unroll
-      for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
-      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      mx *= sl2;
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m = mx;
-      } else {
-        need = mx > m + RESCALE_THRESHOLD;
-        if (need) {
-          alpha = fast_exp2(m - mx);
-          m = mx;
-        }
-      }
-      CE_TICK(2)
-      // P.V(j-1) of this query tile completed before S(j) was even issued, so O is stable here
-      if (__any_sync(0xffffffffu, need)) {
-        l *= alpha;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(o_tmem + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(o_tmem + c * 32, o);
-        }
-      }
-      const float neg_m = -m;
-      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums; 2 MUFU (or the FMA-pipe polynomial) per pair
-      const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
-      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[64];
-      auto exp_pair = [&](int i) {
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t sl2_2 = f2_pack(sl2, sl2);
+      uint64_t negm_2 = f2_pack(-m, -m);
+      // packed fp32 pairs: FFMA2 for the scale-and-shift, FADD2 for the row sums; 2 MUFU (or the FMA-pipe polynomial) per pair
+      auto exp_pair = [&](int i, bool ordered = false) {
         const uint64_t x2 = f2_fma(f2_pack_bits(s[2 * i], s[2 * i + 1]), sl2_2, negm_2);
         float p0, p1;
-        if ((i & 3) < POLY) {
+        if ((i & 7) < POLY8) {
           f2_exp2_poly(x2, p0, p1);
         } else {
           float x0, x1;
           f2_unpack(x2, x0, x1);
-          p0 = fast_exp2(x0);
-          p1 = fast_exp2(x1);
+          p0 = ordered ? fast_exp2_ordered(x0) : fast_exp2(x0);
+          p1 = ordered ? fast_exp2_ordered(x1) : fast_exp2(x1);
         }
         sum2[i & 3] = f2_add(sum2[i & 3], f2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
       };
+      bool first_half_done = false;
+      float mx = 0.f;
+      if (SPEC && j > 0 && valid >= BKV) {
+        // ---- speculative order: columns 0-31 first, the rest of the row lands while they are being exponentiated
+        tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 1; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+        CE_TICK(1)
+        float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          exp_pair(i, true);   // ordered: stays in front of the wait for columns 32-127
+          if (i >= 2) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 16; i < 32; ++i) {
+          exp_pair(i);
+          mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])));
+          const int e = 64 + 4 * (i - 16);   // columns 64-127: four per step
+          mx4[(i + 1) & 3] = fmaxf(mx4[(i + 1) & 3], fmaxf(__uint_as_float(s[e]), __uint_as_float(s[e + 1])));
+          mx4[(i + 2) & 3] = fmaxf(mx4[(i + 2) & 3], fmaxf(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])));
+        }
+        mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+        CE_TICK(2)
+        if (!__any_sync(0xffffffffu, mx > m + RESCALE_THRESHOLD)) {
+          first_half_done = true;
+        } else {  // some row of this warp outgrew the threshold: columns 0-63 again from TMEM (64-127 are still in registers)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sum2[i] = 0ull;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+        tmem_ld_wait();
+        CE_TICK(1)
+        if (valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) s[i] = (i < valid) ? s[i] : 0xff800000u;
+        }
+        float mx8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
+#pragma unroll
+        for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
+        mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        mx *= sl2;
+        CE_TICK(2)
+      }
+      if (!first_half_done) {
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m = mx;
+        } else {
+          need = mx > m + RESCALE_THRESHOLD;
+          if (need) {
+            alpha = fast_exp2(m - mx);
+            m = mx;
+          }
+        }
+        // P.V(j-1) of this query tile completed before S(j) was even issued, so O is stable here
+        if (__any_sync(0xffffffffu, need)) {
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_tmem + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_tmem + c * 32, o);
+          }
+        }
+        negm_2 = f2_pack(-m, -m);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) exp_pair(i);
+      }
       // P (packed bf16, 64 columns) overwrites the first half of this group's S region, published in two halves so that
       // the tensor pipe starts on P.V while the second half is still being exponentiated
-#pragma unroll
-      for (int i = 0; i < 32; ++i) exp_pair(i);
       tc_fence_after();
       tmem_st_32x32(s_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
 #pragma unroll
@@ -304,6 +356,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt]);
       CE_TICK(3)
+      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 1] = clock64();
 #pragma unroll
       for (int i = 40; i < 64; ++i) exp_pair(i);
       tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
@@ -317,6 +370,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + 2 + qt]);
       CE_TICK(4)
+      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 2] = clock64();
     }
     if (timed) {
       for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
@@ -370,23 +424,41 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap2(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap2(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap2(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
-  // developer knob: CE_ATTN_POLY = how many of every 4 exp2 pairs run on the FMA pipe (0..3)
+  // developer knobs: CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..4); CE_ATTN_SPEC=0 turns the
+  // speculative (previous-maximum) order of the softmax off
   static const int poly = [] {
     const char* e = getenv("CE_ATTN_POLY");
     const int v = e ? atoi(e) : 0;
-    return v < 0 ? 0 : (v > 3 ? 3 : v);
+    return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();
-  CE_ENSURE_SMEM(attention2_fwd_kernel<0>, Smem2::total);
-  CE_ENSURE_SMEM(attention2_fwd_kernel<1>, Smem2::total);
-  CE_ENSURE_SMEM(attention2_fwd_kernel<2>, Smem2::total);
-  CE_ENSURE_SMEM(attention2_fwd_kernel<3>, Smem2::total);
+  static const bool spec = [] {
+    const char* e = getenv("CE_ATTN_SPEC");
+    return !(e && e[0] == '0');
+  }();
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-  switch (poly) {
-    case 0: attention2_fwd_kernel<0><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
-    case 1: attention2_fwd_kernel<1><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
-    case 2: attention2_fwd_kernel<2><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
-    default: attention2_fwd_kernel<3><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a); break;
+#define CE_LAUNCH_ATTN2(P, S)                                                                            \
+  do {                                                                                                   \
+    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S>), Smem2::total);                                         \
+    attention2_fwd_kernel<P, S><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);           \
+  } while (0)
+  if (spec) {
+    switch (poly) {
+      case 0: CE_LAUNCH_ATTN2(0, true); break;
+      case 1: CE_LAUNCH_ATTN2(1, true); break;
+      case 2: CE_LAUNCH_ATTN2(2, true); break;
+      case 3: CE_LAUNCH_ATTN2(3, true); break;
+      default: CE_LAUNCH_ATTN2(4, true); break;
+    }
+  } else {
+    switch (poly) {
+      case 0: CE_LAUNCH_ATTN2(0, false); break;
+      case 1: CE_LAUNCH_ATTN2(1, false); break;
+      case 2: CE_LAUNCH_ATTN2(2, false); break;
+      case 3: CE_LAUNCH_ATTN2(3, false); break;
+      default: CE_LAUNCH_ATTN2(4, false); break;
+    }
   }
+#undef CE_LAUNCH_ATTN2
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -311,6 +311,13 @@ __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; exp2(-inf) =
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// same instruction, but ordered against the other volatile asm statements (tcgen05.ld / wait::ld): used where exponentials must be
+// issued BEFORE a later TMEM wait so that they overlap the loads still in flight
+__device__ __forceinline__ float fast_exp2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): one instruction for two lanes of work
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;

@@ -8,7 +8,7 @@ B, H, Lq = 1, 40, 7200
 D = H * 128
 x = torch.randn(B, Lq, 3 * D, device="cuda", dtype=torch.bfloat16)
 out = torch.empty(B, Lq, D, device="cuda", dtype=torch.bfloat16)
-buf = torch.zeros(16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(256, dtype=torch.int64, device="cuda")
 L.check(lib.ce_debug_attention_timing(L.ptr(buf)))
 for _ in range(3):
     L.check(lib.ce_attention_bf16(L.ptr(x), 3 * D, L.ptr(x[..., D:]), 3 * D, L.ptr(x[..., 2 * D:]), 3 * D, L.ptr(out), D, B, H, Lq, Lq, 1 / math.sqrt(128), 0,
@@ -29,3 +29,12 @@ if ver == "5" and t[15]:
     for nm, c in zip(names, t[8:15]):
         print(f"  {nm:28s} {c / max(t[15],1):9.1f} cycles/tile")
     print(f"  {'total':28s} {sum(t[8:15]) / max(t[15],1):9.1f} cycles/tile")
+
+if v2 and ver != "5" and any(t[64:128]):
+    # event log of query tile 0 of block 0, key tiles 16..23 (SM clock): softmax thread: S ready seen, P[0:64) published, P[64:128)
+    # published; issuer thread: P.V first half issued, second half issued, S(j) issued (slot 5 of tile j = the S that tile j consumes)
+    print("event log (cycles relative to 'S(j) seen' of tile 16): tile | S seen | P1 pub | P2 pub || PV1 issued | PV2 issued | S(j) issued")
+    t0 = t[64]
+    for k in range(8):
+        e = t[64 + 8 * k: 64 + 8 * k + 6]
+        print("  j=%d  %7d %7d %7d || %7d %7d %7d" % (16 + k, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0))

@@ -106,7 +106,7 @@ def test_linear_linearity():
     assert torch.equal(outs[2], (A1.float() + A2.float()) @ W.float().t())
 
 
-def run_attention(B, H, Lq, Lk, seed=0, accumulate=False, strided=True):
+def run_attention(B, H, Lq, Lk, seed=0, accumulate=False, strided=True, key_ramp=0.0):
     L = _lib()
     lib = L.lib()
     hd = 128
@@ -121,6 +121,9 @@ def run_attention(B, H, Lq, Lk, seed=0, accumulate=False, strided=True):
         kv = torch.randn(B, Lk, 2 * D, generator=g).bfloat16().cuda()
         k, v = kv[..., :D], kv[..., D:]
         ldq, ldk, ldv = D, 2 * D, 2 * D
+    if key_ramp:  # keys grow along the sequence: the running row maximum keeps jumping by more than the lazy-rescale threshold
+        ramp = (1.0 + key_ramp * torch.arange(Lk, dtype=torch.float32) / Lk).view(1, Lk, 1).cuda()
+        k.copy_((k.float() * ramp).bfloat16())
     prev = torch.randn(B, Lq, D, generator=g).bfloat16().cuda()
     out = prev.clone() if accumulate else torch.zeros(B, Lq, D, dtype=torch.bfloat16, device="cuda")
     scale = 1.0 / math.sqrt(hd)
@@ -143,6 +146,14 @@ def run_attention(B, H, Lq, Lk, seed=0, accumulate=False, strided=True):
                                        (1, 2, 100, 129)])
 def test_attention_self(B, H, Lq, Lk):
     run_attention(B, H, Lq, Lk, seed=Lq + Lk)
+
+
+@gpu
+@pytest.mark.parametrize("Lq,ramp", [(1024, 6.0), (1500, 12.0), (640, -0.9)])
+def test_attention_self_growing_and_shrinking_scores(Lq, ramp):
+    """Exercises the rescale paths of the online softmax (incl. the redo after a failed speculation on the previous maximum):
+    |k| grows (or shrinks) along the keys, so later key tiles raise the row maximum by far more than 2^8 again and again."""
+    run_attention(1, 2, Lq, Lq, seed=Lq, key_ramp=ramp)
 
 
 @gpu
