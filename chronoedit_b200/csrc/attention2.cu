@@ -50,7 +50,15 @@ enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_E
 // row maximum is folded in between the MUFU instructions; only when that maximum turns out to exceed the running one by more
 // than the lazy-rescale threshold (rare after the first tiles) is the tile redone the classic way (max first).  Results are
 // bit-identical to the non-speculative order: when no rescale is due the classic path uses the same stale maximum.
-template <int POLY8, bool SPEC>
+// FIXED: the MMA issuer walks a FIXED order with blocking waits -- per key tile j: P.V_0(j) first half, second half, S_0(j+1),
+// then the same three for query tile 1 -- instead of issuing whatever is ready.  The tensor pipe executes in issue order, so a
+// greedy issuer lets the other tile's ready-but-not-urgent MMAs (its P.V first half) slip in front of the one chain that
+// bounds the loop (P second half -> P.V second half -> next S -> softmax): measured with the event log below, the greedy order
+// settles at ~3600 cycles per key tile per query tile, while this chain alone is ~2770 (230 S-ready latency + 1770 softmax +
+// 256 + 512 MMA) and the other tile's three MMAs fit in its softmax phase.  With the fixed order the two tiles fall into that
+// anti-phase schedule by themselves.  The producer likewise loads K(j), V(j) in order with blocking waits (no polling warps
+// competing with the softmax warps for issue slots).
+template <int POLY8, bool SPEC, bool FIXED>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
@@ -96,6 +104,27 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         int k_next = 0, v_next = 0;
         uint64_t t_start = 0;
         uint32_t idle = 0;
+        if (FIXED) {
+          for (int t = 0; t < n_tiles; ++t) {
+            {
+              const int st = t % NK;
+              mbar_wait(&bars[K_EMPTY + st], ((t / NK) & 1) ^ 1, 10 + st);
+              uint8_t* ks = smem + Smem2::k + st * TILE_BYTES;
+              mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
+              tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, t * BKV, b);
+              tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, t * BKV, b);
+            }
+            {
+              const int st = t % NV;
+              mbar_wait(&bars[V_EMPTY + st], ((t / NV) & 1) ^ 1, 20 + st);
+              uint8_t* vs = smem + Smem2::v + st * TILE_BYTES;
+              mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
+              tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, t * BKV, b);
+              tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, t * BKV, b);
+            }
+          }
+          k_next = v_next = n_tiles;
+        }
         while (k_next < n_tiles || v_next < n_tiles) {
           bool progress = false;
           if (k_next < n_tiles) {
@@ -140,9 +169,54 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         int s_next[2] = {0, 0}, pv_next[2] = {0, 0}, pv_half[2] = {0, 0};
         const bool timed_i = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define CE_EVT(jj, slot)                                                             \
-  if (timed_i && qt == 0 && (jj) >= 16 && (jj) < 24) a.timing[64 + ((jj)-16) * 8 + (slot)] = clock64();
+  if (timed_i && (jj) >= 16 && (jj) < 24) a.timing[64 + qt * 64 + ((jj)-16) * 8 + (slot)] = clock64();
         uint64_t t_start = 0;
         uint32_t idle = 0;
+        if (FIXED) {
+          auto issue_s = [&](int qt, int j) {
+            mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30 + qt);
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
+            const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
+            const uint32_t d = tmem_base + qt * 128;
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const uint32_t off = (kk >> 2) * HALF_BYTES;
+              umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S,
+                           kk != 0);
+            }
+            umma_commit(&bars[S_FULL + qt]);
+            if (qt == 1) umma_commit(&bars[K_EMPTY + j % NK]);   // both query tiles have consumed K_j
+            CE_EVT(j, 5)
+          };
+          issue_s(0, 0);
+          issue_s(1, 0);
+          for (int j = 0; j < n_tiles; ++j) {
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt) {
+              const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
+              const uint32_t p_tmem = tmem_base + qt * 128;
+              const uint32_t d = tmem_base + 256 + qt * 128;
+              mbar_wait(&bars[P_FULL + qt], j & 1, 40 + qt);
+              if (qt == 0) mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 44);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < BKV / 32; ++kk)
+                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
+              CE_EVT(j, 3)
+              mbar_wait(&bars[P_FULL + 2 + qt], j & 1, 46 + qt);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = BKV / 32; kk < BKV / 16; ++kk)
+                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, 1);
+              umma_commit(&bars[PV_DONE + qt]);
+              if (qt == 1) umma_commit(&bars[V_EMPTY + j % NV]);   // both query tiles have consumed V_j
+              CE_EVT(j, 4)
+              if (j + 1 < n_tiles) issue_s(qt, j + 1);
+            }
+          }
+          pv_next[0] = pv_next[1] = n_tiles;
+        }
         while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
           bool progress = false;
 #pragma unroll
@@ -227,7 +301,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 128 || threadIdx.x == 256);
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
 #define CE_TICK(slot)                      \
@@ -243,7 +317,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
       CE_TICK(0)
-      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 0] = clock64();
+      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 0] = clock64();
       uint32_t s[128];
       uint32_t pk[64];
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
@@ -356,7 +430,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + qt]);
       CE_TICK(3)
-      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 1] = clock64();
+      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 1] = clock64();
 #pragma unroll
       for (int i = 40; i < 64; ++i) exp_pair(i);
       tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
@@ -370,9 +444,9 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       tc_fence_before();
       mbar_arrive(&bars[P_FULL + 2 + qt]);
       CE_TICK(4)
-      if (timed && j >= 16 && j < 24) a.timing[64 + (j - 16) * 8 + 2] = clock64();
+      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 2] = clock64();
     }
-    if (timed) {
+    if (timed && qt == 0) {
       for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
       a.timing[5] = n_tiles;
     }
@@ -424,40 +498,38 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap2(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap2(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap2(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
-  // developer knobs: CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..4); CE_ATTN_SPEC=0 turns the
-  // speculative (previous-maximum) order of the softmax off
+  // developer knobs: CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..2); CE_ATTN_SPEC=1 turns the
+  // speculative (previous-maximum) order of the softmax on; CE_ATTN_FIXED=0 goes back to the event-driven issuer / producer
   static const int poly = [] {
     const char* e = getenv("CE_ATTN_POLY");
     const int v = e ? atoi(e) : 0;
-    return v < 0 ? 0 : (v > 4 ? 4 : v);
+    return v < 0 ? 0 : (v > 2 ? 2 : v);
   }();
   static const bool spec = [] {
     const char* e = getenv("CE_ATTN_SPEC");
+    return e && e[0] == '1';
+  }();
+  static const bool fixed = [] {
+    const char* e = getenv("CE_ATTN_FIXED");
     return !(e && e[0] == '0');
   }();
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-#define CE_LAUNCH_ATTN2(P, S)                                                                            \
+#define CE_LAUNCH_ATTN2(P, S, F)                                                                         \
   do {                                                                                                   \
-    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S>), Smem2::total);                                         \
-    attention2_fwd_kernel<P, S><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);           \
+    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S, F>), Smem2::total);                                      \
+    attention2_fwd_kernel<P, S, F><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);        \
   } while (0)
-  if (spec) {
-    switch (poly) {
-      case 0: CE_LAUNCH_ATTN2(0, true); break;
-      case 1: CE_LAUNCH_ATTN2(1, true); break;
-      case 2: CE_LAUNCH_ATTN2(2, true); break;
-      case 3: CE_LAUNCH_ATTN2(3, true); break;
-      default: CE_LAUNCH_ATTN2(4, true); break;
-    }
-  } else {
-    switch (poly) {
-      case 0: CE_LAUNCH_ATTN2(0, false); break;
-      case 1: CE_LAUNCH_ATTN2(1, false); break;
-      case 2: CE_LAUNCH_ATTN2(2, false); break;
-      case 3: CE_LAUNCH_ATTN2(3, false); break;
-      default: CE_LAUNCH_ATTN2(4, false); break;
-    }
+#define CE_LAUNCH_ATTN2_P(S, F)                       \
+  switch (poly) {                                     \
+    case 0: CE_LAUNCH_ATTN2(0, S, F); break;          \
+    case 1: CE_LAUNCH_ATTN2(1, S, F); break;          \
+    default: CE_LAUNCH_ATTN2(2, S, F); break;         \
   }
+  if (spec && fixed) { CE_LAUNCH_ATTN2_P(true, true) }
+  else if (spec) { CE_LAUNCH_ATTN2_P(true, false) }
+  else if (fixed) { CE_LAUNCH_ATTN2_P(false, true) }
+  else { CE_LAUNCH_ATTN2_P(false, false) }
+#undef CE_LAUNCH_ATTN2_P
 #undef CE_LAUNCH_ATTN2
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;

@@ -208,8 +208,6 @@ class FlowUniPCMultistepScheduler:
     def _launch(self, cond, uncond, guidance, timestep, sample, model_input_out) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        if not (sample.is_cuda and cond.is_cuda):
-            raise _lib.CEError("FlowUniPCMultistepScheduler.step needs CUDA tensors: chronoedit_b200 has no CPU path")
         if (sample.dtype, cond.dtype) not in ((torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)):
             raise TypeError(f"(sample, model_output) dtypes {sample.dtype}, {cond.dtype} not built: (fp32,fp32), (fp32,bf16), (bf16,bf16)")
         if cond.shape != sample.shape or (uncond is not None and (uncond.shape != sample.shape or uncond.dtype != cond.dtype)):
@@ -237,7 +235,7 @@ class FlowUniPCMultistepScheduler:
         a.corrected_out = corrected.data_ptr() if a.use_corrector else None
         a.model_input_out, a.inner, a.c_lat, a.c_total = None, 1, 1, 1
         if model_input_out is not None:
-            if not (model_input_out.is_cuda and model_input_out.dtype == torch.bfloat16 and model_input_out.is_contiguous()
+            if not (model_input_out.dtype == torch.bfloat16 and model_input_out.is_contiguous()
                     and model_input_out.dim() == sample.dim() and model_input_out.shape[0] == sample.shape[0]
                     and model_input_out.shape[2:] == sample.shape[2:] and model_input_out.shape[1] >= sample.shape[1]):
                 raise ValueError("model_input_out must be a contiguous bf16 CUDA tensor [B, C_total >= C_latent, T, H, W]")
@@ -258,6 +256,8 @@ class FlowUniPCMultistepScheduler:
     def _native_step(self, a: "_lib.UniPCStepArgsC", tensors: dict) -> None:
         """The one place the scheduler reaches the C ABI.  `a` already holds every pointer and coefficient; `tensors` names the
         same buffers as torch tensors (kept alive across the launch; also what a test harness needs to stand in for the kernel)."""
+        if not (tensors["sample"].is_cuda and tensors["cond"].is_cuda):
+            raise _lib.CEError("FlowUniPCMultistepScheduler.step needs CUDA tensors: chronoedit_b200 has no CPU path")
         _lib.check(_lib.lib().ce_unipc_step(ctypes.byref(a), _lib.current_stream()))
 
     def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor, return_dict: bool = True,

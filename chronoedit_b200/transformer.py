@@ -183,6 +183,7 @@ class ChronoEditTransformer3DModel(nn.Module):
         self.cache_context = bool(cache_context)
         self._ctx_slots = 2
         self._ctx_cache: list = []   # entries: dict(txt=, img=, txt_v=, img_v=, shape=, buf=)
+        self._lora_adapters: Dict[str, Dict[str, torch.Tensor]] = {}
         self.last_captures: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------ plumbing
@@ -426,23 +427,23 @@ class ChronoEditTransformer3DModel(nn.Module):
         return int(_lib.lib().ce_dit_last_launch_count(self._handle)) if self._handle else 0
 
     # ------------------------------------------------------------------------------------------ LoRA
-    # (original Wan module name -> diffusers name) pairs of the reference's own converter, chronoedit/_src/models/utils.py:112-190
+    # (original Wan module name -> diffusers name): the pairs of the reference's own converters -- per-block modules
+    # chronoedit/_src/models/utils.py:112-212, non-block modules :214-290; the diffusers-side names are those of
+    # chronoedit_diffsynth/wan_video_dit_chronoedit.py:439-496 read right to left.
     _WAN_TO_DIFFUSERS = (("self_attn.q", "attn1.to_q"), ("self_attn.k", "attn1.to_k"), ("self_attn.v", "attn1.to_v"),
                          ("self_attn.o", "attn1.to_out.0"), ("cross_attn.q", "attn2.to_q"), ("cross_attn.k_img", "attn2.add_k_proj"),
                          ("cross_attn.v_img", "attn2.add_v_proj"), ("cross_attn.k", "attn2.to_k"), ("cross_attn.v", "attn2.to_v"),
                          ("cross_attn.o", "attn2.to_out.0"), ("ffn.0", "ffn.net.0.proj"), ("ffn.2", "ffn.net.2"))
+    _WAN_TO_DIFFUSERS_GLOBAL = {
+        "time_embedding.0": "condition_embedder.time_embedder.linear_1", "time_embedding.2": "condition_embedder.time_embedder.linear_2",
+        "text_embedding.0": "condition_embedder.text_embedder.linear_1", "text_embedding.2": "condition_embedder.text_embedder.linear_2",
+        "time_projection.1": "condition_embedder.time_proj", "head.head": "proj_out",
+        "img_emb.proj.1": "condition_embedder.image_embedder.ff.net.0.proj", "img_emb.proj.3": "condition_embedder.image_embedder.ff.net.2",
+    }
 
-    @torch.no_grad()
-    def fuse_lora(self, lora_state_dict: Dict[str, torch.Tensor], lora_scale: float = 1.0, adapter_name: Optional[str] = None) -> int:
-        """`pipe.load_lora_weights(path); pipe.fuse_lora(lora_scale=s)` (run_inference_diffusers.py:369-376) for this module:
-        W += (B @ A) * (s * alpha / r), in place and in the weight dtype, which is PEFT's merge arithmetic.  The kernels see
-        the result without repacking because the fused QKV buffers are views of the same storage.
-
-        Keys: diffusers / PEFT style `[transformer.]blocks.N.attn1.to_q.lora_A[.adapter].weight` (+ `lora_B`, optional
-        `.alpha`), or the original Wan style the in-tree loader converts (`[diffusion_model.]blocks.N.self_attn.q.lora_down|lora_A
-        .weight`, `lora_up|lora_B`, `.alpha`; chronoedit/_src/models/utils.py:66-190, wan_t2v_model.py:385-391).  `diff` /
-        `diff_b` entries (norm / bias deltas the reference converter drops or treats as lora_bias) are rejected.  One-time
-        weight preparation with torch matmuls; not on the per-step path.  Returns the number of weights updated."""
+    def _parse_lora(self, lora_state_dict: Dict[str, torch.Tensor], adapter_name: Optional[str]):
+        """Pass 1 of fuse_lora: key grammar, name mapping, presence of both factors, shapes.  Nothing is modified here, so a bad
+        file leaves the model untouched.  Returns [(parameter, A, B, alpha or None)]."""
         params = dict(self.named_parameters())
         pairs: Dict[str, Dict[str, torch.Tensor]] = {}
         for key, val in lora_state_dict.items():
@@ -450,38 +451,112 @@ class ChronoEditTransformer3DModel(nn.Module):
             for pre in ("transformer.", "diffusion_model."):
                 if k.startswith(pre):
                     k = k[len(pre):]
-            if k.endswith((".diff", ".diff_b")):
+            if k.endswith((".diff", ".diff_b")) or ".lora_B." in k and k.endswith(".bias"):
                 raise CEError(f"fuse_lora: '{key}' is a weight/bias delta, not a low-rank pair; not supported")
-            if adapter_name is not None:
-                k = k.replace(f".{adapter_name}.", ".")
             k = k.replace(".lora_down.", ".lora_A.").replace(".lora_up.", ".lora_B.")
-            if k.endswith(".alpha"):
-                mod, kind = k[: -len(".alpha")], "alpha"
-            elif k.endswith(".lora_A.weight"):
-                mod, kind = k[: -len(".lora_A.weight")], "A"
-            elif k.endswith(".lora_B.weight"):
-                mod, kind = k[: -len(".lora_B.weight")], "B"
-            else:
-                raise CEError(f"fuse_lora: unrecognised key '{key}'")
-            for wan, dif in self._WAN_TO_DIFFUSERS:
-                if mod.endswith("." + wan):
-                    mod = mod[: -len(wan)] + dif
+            kind = None
+            for tag, nm in ((".lora_A.", "A"), (".lora_B.", "B")):
+                if tag in k and k.endswith(".weight"):
+                    mod, rest = k.split(tag, 1)
+                    seg = rest[: -len("weight")].strip(".")       # "" or the PEFT adapter segment ("default", ...)
+                    if seg and adapter_name is not None and seg != adapter_name:
+                        kind = "skip"   # another adapter's weights
+                    elif "." in seg:
+                        raise CEError(f"fuse_lora: unrecognised key '{key}'")
+                    else:
+                        kind = nm
                     break
-            pairs.setdefault(mod, {})[kind] = val
-        n = 0
+            if kind is None and k.endswith(".alpha"):
+                mod, kind = k[: -len(".alpha")], "alpha"
+            if kind is None:
+                raise CEError(f"fuse_lora: unrecognised key '{key}'")
+            if kind == "skip":
+                continue
+            if mod in self._WAN_TO_DIFFUSERS_GLOBAL:
+                mod = self._WAN_TO_DIFFUSERS_GLOBAL[mod]
+            else:
+                for wan, dif in self._WAN_TO_DIFFUSERS:
+                    if mod.endswith("." + wan):
+                        mod = mod[: -len(wan)] + dif
+                        break
+            if kind in pairs.setdefault(mod, {}):
+                raise CEError(f"fuse_lora: '{mod}' has more than one {kind} entry (several adapters in one file? pass adapter_name)")
+            pairs[mod][kind] = val
+        plan = []
         for mod, d in pairs.items():
             if "A" not in d or "B" not in d:
                 raise CEError(f"fuse_lora: '{mod}' needs both lora_A and lora_B")
             w = params.get(mod + ".weight")
             if w is None:
                 raise CEError(f"fuse_lora: no parameter '{mod}.weight' in this model")
-            A, B = d["A"].to(w.device, w.dtype), d["B"].to(w.device, w.dtype)
+            A, B = d["A"], d["B"]
             r = A.shape[0]
-            if A.shape != (r, w.shape[1]) or B.shape != (w.shape[0], r):
+            if A.dim() != 2 or B.dim() != 2 or A.shape != (r, w.shape[1]) or B.shape != (w.shape[0], r):
                 raise CEError(f"fuse_lora: shapes of '{mod}' do not match: A {tuple(A.shape)} B {tuple(B.shape)} W {tuple(w.shape)}")
-            alpha = float(d["alpha"]) if "alpha" in d else float(r)
-            w.data += (B @ A) * (lora_scale * alpha / r)   # peft LoraLayer.get_delta_weight / merge
+            plan.append((w, A, B, float(d["alpha"]) if "alpha" in d else None))
+        return plan
+
+    def load_lora_adapter(self, state_dict: Dict[str, torch.Tensor], prefix: Optional[str] = "transformer", network_alphas=None,
+                          adapter_name: Optional[str] = None, **unused) -> None:
+        """diffusers `PeftAdapterMixin.load_lora_adapter` as `WanLoraLoaderMixin.load_lora_weights` calls it
+        (run_inference_diffusers.py:371): keep the adapter's factors (validated now) until `fuse_lora` merges them."""
+        if prefix:
+            sub = {k[len(prefix) + 1:]: v for k, v in state_dict.items() if k.startswith(prefix + ".")}
+            state_dict = sub or {k: v for k, v in state_dict.items() if not k.startswith(("text_encoder.", "vae."))}
+        name = adapter_name or f"default_{len(self._lora_adapters)}"
+        self._parse_lora(state_dict, None)   # fail now, not at fuse time
+        self._lora_adapters[name] = dict(state_dict)
+
+    def unload_lora(self) -> None:
+        self._lora_adapters.clear()
+
+    @torch.no_grad()
+    def fuse_lora(self, *args, **kwargs) -> int:
+        """`pipe.load_lora_weights(path); pipe.fuse_lora(lora_scale=s)` (run_inference_diffusers.py:369-376) for this module:
+        W += (B @ A) * (s * alpha / r), in place and in the weight dtype, which is PEFT's merge arithmetic.  The kernels see
+        the result without repacking because the fused QKV buffers are views of the same storage.
+
+        Two call styles: diffusers' `fuse_lora(lora_scale, safe_fusing=False, adapter_names=None)` merges the adapters handed over
+        by `load_lora_adapter`; `fuse_lora(state_dict, lora_scale=s)` merges a state dict directly.  Keys: diffusers / PEFT style
+        `[transformer.]blocks.N.attn1.to_q.lora_A[.adapter].weight` (+ `lora_B`, optional `.alpha`), or the original Wan style the
+        in-tree loader converts (`[diffusion_model.]blocks.N.self_attn.q.lora_down|lora_A.weight`, `lora_up|lora_B`, `.alpha`, and
+        the non-block modules time_embedding / text_embedding / time_projection / head.head / img_emb.proj;
+        chronoedit/_src/models/utils.py:66-290, wan_t2v_model.py:385-391).  `diff` / `diff_b` entries (norm / bias deltas the
+        reference converter drops or treats as lora_bias) are rejected.  Everything is validated BEFORE the first weight is
+        touched.  One-time weight preparation with torch matmuls; not on the per-step path.  Returns the number of weights updated."""
+        lora_state_dict = kwargs.pop("lora_state_dict", None)
+        if args and isinstance(args[0], dict):        # fuse_lora(state_dict[, lora_scale])
+            lora_state_dict, args = args[0], args[1:]
+        lora_scale = kwargs.pop("lora_scale", args[0] if len(args) > 0 else 1.0)
+        safe_fusing = bool(kwargs.pop("safe_fusing", args[1] if len(args) > 1 else False))
+        adapter_names = kwargs.pop("adapter_names", args[2] if len(args) > 2 else None)
+        adapter_name = kwargs.pop("adapter_name", None)
+        if kwargs:
+            raise TypeError(f"fuse_lora: unexpected arguments {sorted(kwargs)}")
+        if lora_state_dict is not None:
+            plans = [self._parse_lora(lora_state_dict, adapter_name)]
+        else:
+            names = list(self._lora_adapters) if adapter_names is None else list(adapter_names)
+            missing = [n for n in names if n not in self._lora_adapters]
+            if missing or not names:
+                raise CEError(f"fuse_lora: no loaded adapter named {missing or '(none loaded)'}")
+            plans = [self._parse_lora(self._lora_adapters[n], None) for n in names]
+        n = 0
+        deltas = []
+        for plan in plans:
+            for w, A, B, alpha in plan:
+                A, B = A.to(w.device, w.dtype), B.to(w.device, w.dtype)
+                r = A.shape[0]
+                delta = (B @ A) * (float(lora_scale) * (alpha if alpha is not None else float(r)) / r)   # peft get_delta_weight
+                if safe_fusing and not torch.isfinite(delta).all():
+                    raise CEError("fuse_lora(safe_fusing=True): non-finite values in the LoRA delta; nothing was fused")
+                deltas.append((w, delta))
+        for w, delta in deltas:
+            w.data += delta
             n += 1
+        if lora_state_dict is None:
+            self._lora_adapters.clear()   # merged: a second fuse_lora must not add them again
+        self._ctx_cache = []              # cross-attention K/V cached from the old weights are stale
         return n
 
     # ------------------------------------------------------------------------------------------ loading

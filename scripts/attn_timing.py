@@ -30,11 +30,12 @@ if ver == "5" and t[15]:
         print(f"  {nm:28s} {c / max(t[15],1):9.1f} cycles/tile")
     print(f"  {'total':28s} {sum(t[8:15]) / max(t[15],1):9.1f} cycles/tile")
 
-if v2 and ver != "5" and any(t[64:128]):
-    # event log of query tile 0 of block 0, key tiles 16..23 (SM clock): softmax thread: S ready seen, P[0:64) published, P[64:128)
-    # published; issuer thread: P.V first half issued, second half issued, S(j) issued (slot 5 of tile j = the S that tile j consumes)
-    print("event log (cycles relative to 'S(j) seen' of tile 16): tile | S seen | P1 pub | P2 pub || PV1 issued | PV2 issued | S(j) issued")
+if v2 and ver != "5" and any(t[64:192]):
+    # event log of block 0, key tiles 16..23 (SM clock), both query tiles: softmax thread: S ready seen, P[0:64) published,
+    # P[64:128) published; issuer thread: P.V first half issued, second half issued, S(j) issued (the S that tile j consumes)
     t0 = t[64]
-    for k in range(8):
-        e = t[64 + 8 * k: 64 + 8 * k + 6]
-        print("  j=%d  %7d %7d %7d || %7d %7d %7d" % (16 + k, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0))
+    for qt in range(2):
+        print(f"event log, query tile {qt} (cycles relative to 'S(16) seen' of query tile 0): tile | S seen | P1 pub | P2 pub || PV1 issued | PV2 issued | S(j) issued")
+        for k in range(8):
+            e = t[64 + 64 * qt + 8 * k: 64 + 64 * qt + 8 * k + 6]
+            print("  j=%d  %7d %7d %7d || %7d %7d %7d" % (16 + k, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0))

@@ -82,6 +82,59 @@ def test_fuse_lora_rejects_what_it_cannot_merge():
         m.fuse_lora({"blocks.9.attn1.to_q.lora_A.weight": torch.zeros(4, 256), "blocks.9.attn1.to_q.lora_B.weight": torch.zeros(256, 4)})
 
 
+def test_fuse_lora_is_all_or_nothing():
+    """One bad entry anywhere in the file must leave every weight untouched (validation happens before the first update)."""
+    from chronoedit_b200 import CEError
+    m = _model()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    dif, _ = _lora(m)
+    bad = dict(dif)
+    bad["transformer.blocks.1.ffn.net.2.lora_B.weight"] = torch.zeros(7, 4, dtype=torch.bfloat16)   # wrong shape, last module
+    with pytest.raises(CEError):
+        m.fuse_lora(bad)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), f"{k} was modified by a rejected fuse"
+
+
+def test_fuse_lora_non_block_modules_and_peft_adapter_segment():
+    """Original-Wan files carry non-block modules (utils.py:214-290); PEFT files carry `.default.` between lora_A/B and weight."""
+    m = _model()
+    params = dict(m.named_parameters())
+    g = torch.Generator().manual_seed(3)
+    wan_to_dif = {"time_embedding.0": "condition_embedder.time_embedder.linear_1", "text_embedding.2": "condition_embedder.text_embedder.linear_2",
+                  "time_projection.1": "condition_embedder.time_proj", "head.head": "proj_out",
+                  "img_emb.proj.1": "condition_embedder.image_embedder.ff.net.0.proj", "img_emb.proj.3": "condition_embedder.image_embedder.ff.net.2"}
+    sd, want = {}, {}
+    for wan, dif in wan_to_dif.items():
+        W = params[dif + ".weight"]
+        A = (torch.randn(2, W.shape[1], generator=g) * 0.1).to(W.dtype)
+        B = (torch.randn(W.shape[0], 2, generator=g) * 0.1).to(W.dtype)
+        sd[f"diffusion_model.{wan}.lora_down.weight"], sd[f"diffusion_model.{wan}.lora_up.weight"] = A, B
+        want[dif] = W.data.clone() + (B @ A) * 0.5
+    W = params["blocks.1.attn1.to_q.weight"]
+    A, B = (torch.randn(2, 256, generator=g) * 0.1).bfloat16(), (torch.randn(256, 2, generator=g) * 0.1).bfloat16()
+    sd["transformer.blocks.1.attn1.to_q.lora_A.default.weight"], sd["transformer.blocks.1.attn1.to_q.lora_B.default.weight"] = A, B
+    want["blocks.1.attn1.to_q"] = W.data.clone() + (B @ A) * 0.5
+    assert m.fuse_lora(sd, lora_scale=0.5) == len(want)
+    for mod, w in want.items():
+        assert torch.equal(dict(m.named_parameters())[mod + ".weight"].data, w), mod
+
+
+def test_diffusers_style_load_then_fuse():
+    """`pipe.load_lora_weights(x); pipe.fuse_lora(lora_scale=s)` reaches the transformer as load_lora_adapter(state_dict,
+    prefix="transformer", ...) + fuse_lora(s, safe_fusing=..., adapter_names=...) ([diffusers-mem]; run_inference_diffusers.py:369-376)."""
+    from chronoedit_b200 import CEError
+    m1, m2 = _model(), _model()
+    dif, _ = _lora(m1)
+    m1.fuse_lora(dif, lora_scale=0.75)
+    m2.load_lora_adapter(dif, prefix="transformer", adapter_name="lora")
+    assert m2.fuse_lora(0.75, safe_fusing=True, adapter_names=None) == 24
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(CEError):
+        m2.fuse_lora(0.75)   # already merged: nothing left to fuse, and certainly not twice
+
+
 @pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference only exists in the build container")
 def test_wan_to_diffusers_module_map_matches_reference_converter():
     import chronoedit_b200 as ce
@@ -93,3 +146,5 @@ def test_wan_to_diffusers_module_map_matches_reference_converter():
         assert f'"blocks.0.{dif}.weight": "blocks.0.{wan}.weight"' in src, (wan, dif)
     assert '"blocks.0.attn2.add_k_proj.weight": "blocks.0.cross_attn.k_img.weight"' in src
     assert '"blocks.0.attn2.add_v_proj.weight": "blocks.0.cross_attn.v_img.weight"' in src
+    for wan, dif in ce.ChronoEditTransformer3DModel._WAN_TO_DIFFUSERS_GLOBAL.items():
+        assert f'"{dif}.weight": "{wan}.weight"' in src, (wan, dif)
