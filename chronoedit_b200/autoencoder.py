@@ -307,17 +307,141 @@ class AutoencoderKLWan(nn.Module):
     def launches(self) -> int:
         return int(_lib.lib().ce_vae_last_launch_count(self._handle)) if self._handle else 0
 
-    # ------------------------------------------------------------------------------------------ checkpoint names
-    @staticmethod
-    def diffusers_key_map(num_res_blocks: int = 2) -> Dict[str, str]:
-        """Best-effort map diffusers AutoencoderKLWan key prefix -> in-tree twin prefix.  diffusers 0.35.2 is not on this
-        box, so this map is restated from memory ([diffusers-mem]) and is NOT verified against a real
-        checkpoint; `load_state_dict` fails loudly on any unmapped key."""
-        m = {"quant_conv": "conv1", "post_quant_conv": "conv2", "encoder.conv_in": "encoder.conv1", "decoder.conv_in": "decoder.conv1",
-             "encoder.norm_out": "encoder.head.0", "encoder.conv_out": "encoder.head.2", "decoder.norm_out": "decoder.head.0",
-             "decoder.conv_out": "decoder.head.2"}
+    # ------------------------------------------------------------------------------------------ checkpoint names / loading
+    @classmethod
+    def diffusers_key_map(cls, base_dim: int = 96, z_dim: int = 16, dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2,
+                          temperal_downsample=(False, True, True)) -> Dict[str, str]:
+        """COMPLETE map  diffusers `AutoencoderKLWan` parameter name -> in-tree twin (`WanVAE_`) parameter name, generated from
+        the architecture (one entry per parameter; `load_state_dict` / `from_pretrained` refuse anything unmapped or missing).
+
+        diffusers 0.35.2 is not on this box, so the diffusers side is restated from its published module tree ([diffusers-mem],
+        SURVEY.md section 8c): `encoder.conv_in`, flat `encoder.down_blocks.N` (WanResidualBlock: norm1 / conv1 / norm2 / conv2 /
+        conv_shortcut; WanResample: resample.1 / time_conv), `{encoder,decoder}.mid_block.{resnets.0, attentions.0, resnets.1}`,
+        `norm_out` / `conv_out`, `quant_conv` / `post_quant_conv`, and `decoder.up_blocks.I.{resnets.R, upsamplers.0}` --
+        the same renames the Wan -> diffusers conversion applies to the original checkpoint whose names the twin keeps
+        (wan2pt1.py:262-500)."""
+        res = {"norm1.gamma": "residual.0.gamma", "conv1.weight": "residual.2.weight", "conv1.bias": "residual.2.bias",
+               "norm2.gamma": "residual.3.gamma", "conv2.weight": "residual.6.weight", "conv2.bias": "residual.6.bias",
+               "conv_shortcut.weight": "shortcut.weight", "conv_shortcut.bias": "shortcut.bias"}
+        same = ("resample.1.weight", "resample.1.bias", "time_conv.weight", "time_conv.bias")
+        attn = ("norm.gamma", "to_qkv.weight", "to_qkv.bias", "proj.weight", "proj.bias")
+        twin = _param_shapes(base_dim, z_dim, tuple(dim_mult), num_res_blocks, tuple(temperal_downsample))
+        m: Dict[str, str] = {}
+
+        def put(dkey, tkey):
+            if tkey in twin:
+                m[dkey] = tkey
+
+        for suf in ("weight", "bias"):
+            put(f"quant_conv.{suf}", f"conv1.{suf}")
+            put(f"post_quant_conv.{suf}", f"conv2.{suf}")
+            for side in ("encoder", "decoder"):
+                put(f"{side}.conv_in.{suf}", f"{side}.conv1.{suf}")
+                put(f"{side}.conv_out.{suf}", f"{side}.head.2.{suf}")
         for side in ("encoder", "decoder"):
-            m[f"{side}.mid_block.resnets.0"] = f"{side}.middle.0"
-            m[f"{side}.mid_block.attentions.0"] = f"{side}.middle.1"
-            m[f"{side}.mid_block.resnets.1"] = f"{side}.middle.2"
+            put(f"{side}.norm_out.gamma", f"{side}.head.0.gamma")
+            for dn, tn in (("mid_block.resnets.0", "middle.0"), ("mid_block.resnets.1", "middle.2")):
+                for dk, tk in res.items():
+                    put(f"{side}.{dn}.{dk}", f"{side}.{tn}.{tk}")
+            for k in attn:
+                put(f"{side}.mid_block.attentions.0.{k}", f"{side}.middle.1.{k}")
+        n_stage = len(dim_mult)
+        idx = 0   # encoder: both sides keep ONE flat list in the same order (res x num_res_blocks, then the resample)
+        for i in range(n_stage):
+            for _ in range(num_res_blocks):
+                for dk, tk in res.items():
+                    put(f"encoder.down_blocks.{idx}.{dk}", f"encoder.downsamples.{idx}.{tk}")
+                idx += 1
+            if i != n_stage - 1:
+                for k in same:
+                    put(f"encoder.down_blocks.{idx}.{k}", f"encoder.downsamples.{idx}.{k}")
+                idx += 1
+        idx = 0   # decoder: diffusers groups each stage into a WanUpBlock (resnets + upsamplers), the twin keeps a flat list
+        for i in range(n_stage):
+            for r in range(num_res_blocks + 1):
+                for dk, tk in res.items():
+                    put(f"decoder.up_blocks.{i}.resnets.{r}.{dk}", f"decoder.upsamples.{idx}.{tk}")
+                idx += 1
+            if i != n_stage - 1:
+                for k in same:
+                    put(f"decoder.up_blocks.{i}.upsamplers.0.{k}", f"decoder.upsamples.{idx}.{k}")
+                idx += 1
+        missing = sorted(set(twin) - set(m.values()))
+        if missing or len(set(m.values())) != len(m):
+            raise CEError(f"diffusers_key_map is not a bijection onto the twin's parameters (first missing: {missing[:1]})")
         return m
+
+    def _map_from_config(self) -> Dict[str, str]:
+        c = self.config
+        return self.diffusers_key_map(c.base_dim, c.z_dim, tuple(c.dim_mult), c.num_res_blocks, tuple(c.temperal_downsample))
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts the twin's names (`encoder.downsamples.0.residual.2.weight`, ...) or a diffusers `AutoencoderKLWan` state dict
+        (`encoder.down_blocks.0.conv1.weight`, ...), recognised by `encoder.conv_in.weight`.  A diffusers dict must map
+        completely: any unmapped or missing key is an error (strict or not), because a silently half-loaded VAE decodes garbage."""
+        if "encoder.conv_in.weight" in state_dict or "decoder.conv_in.weight" in state_dict or "quant_conv.weight" in state_dict:
+            kmap = self._map_from_config()
+            unknown = sorted(k for k in state_dict if k not in kmap)
+            absent = sorted(k for k in kmap if k not in state_dict)
+            if unknown or absent:
+                raise CEError(f"diffusers VAE state dict does not match the architecture: {len(unknown)} unmapped (first: {unknown[:1]}), "
+                              f"{len(absent)} missing (first: {absent[:1]})")
+            own = dict(self.named_parameters())
+            converted = {}
+            for k, v in state_dict.items():
+                t = kmap[k]
+                if tuple(v.shape) != tuple(own[t].shape):
+                    if v.numel() != own[t].numel():
+                        raise CEError(f"shape of '{k}' {tuple(v.shape)} does not match '{t}' {tuple(own[t].shape)}")
+                    v = v.reshape(own[t].shape)
+                converted[t] = v
+            state_dict = converted
+        self._is_packed = False
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def diffusers_state_dict(self) -> Dict[str, torch.Tensor]:
+        """The parameters under their diffusers names (inverse of the map above)."""
+        own = dict(self.named_parameters())
+        return {d: own[t].data for d, t in self._map_from_config().items()}
+
+    @classmethod
+    def from_config(cls, config: Dict, **kw) -> "AutoencoderKLWan":
+        fields = ("base_dim", "z_dim", "dim_mult", "num_res_blocks", "attn_scales", "temperal_downsample", "dropout", "latents_mean",
+                  "latents_std")
+        args = {k: config[k] for k in fields if k in config}
+        for k in ("dim_mult", "attn_scales", "temperal_downsample"):
+            if k in args:
+                args[k] = tuple(args[k])
+        return cls(**args, **kw)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, torch_dtype: torch.dtype = torch.bfloat16,
+                        device=None, **unused) -> "AutoencoderKLWan":
+        """`AutoencoderKLWan.from_pretrained(model_id, subfolder="vae", torch_dtype=torch.bfloat16)` (run_inference_diffusers.py:341-345)
+        for a LOCAL diffusers checkpoint directory: config.json + diffusion_pytorch_model[.safetensors | sharded index].  Also accepts a
+        directory / file holding the original `Wan2.1_VAE.pth`-style names (the twin's)."""
+        import json
+        import os
+
+        from safetensors import safe_open
+
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        cfg = {}
+        cfg_path = os.path.join(root, "config.json")
+        if os.path.exists(cfg_path):
+            with open(cfg_path) as f:
+                cfg = json.load(f)
+        model = cls.from_config(cfg, torch_dtype=torch_dtype, device=device or "cpu")
+        index = os.path.join(root, "diffusion_pytorch_model.safetensors.index.json")
+        if os.path.exists(index):
+            with open(index) as f:
+                files = sorted(set(json.load(f)["weight_map"].values()))
+        else:
+            files = ["diffusion_pytorch_model.safetensors"]
+        sd = {}
+        for fn in files:
+            with safe_open(os.path.join(root, fn), framework="pt", device="cpu") as sf:
+                for k in sf.keys():
+                    sd[k] = sf.get_tensor(k)
+        model.load_state_dict({k: v.to(torch.bfloat16) for k, v in sd.items()}, strict=True)
+        return model
