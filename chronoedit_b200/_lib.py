@@ -64,6 +64,13 @@ SIGNATURES = {
     "ce_dit_host_staging_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "ce_dit_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "ce_dit_forward_host_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "ce_dit_host_staging_sample_offset": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "ce_dit_set_weight_fp32": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "ce_dit_fp32_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "ce_dit_forward_fp32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_int64, c_void_p, c_void_p]),
     "ce_dit_last_launch_count": (c_int64, [c_void_p]),
     "ce_dit_profile_begin": (c_int, [c_void_p, c_int]),
     "ce_dit_profile_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

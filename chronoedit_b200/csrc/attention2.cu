@@ -91,7 +91,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (event-driven)
       if (lane == 0) {
@@ -161,8 +161,8 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer (event-driven)
-      if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer (one elected lane)
+      if (elect_one_sync()) {
         constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major, smem) x K^T (K-major, smem)
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
         mbar_wait(&bars[Q_FULL], 0, 1);
@@ -173,42 +173,51 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         uint64_t t_start = 0;
         uint32_t idle = 0;
         if (FIXED) {
-          auto issue_s = [&](int qt, int j) {
+          // descriptors are computed AHEAD of the waits (the waits are slack time); the issue itself is one asm statement per
+          // group of MMAs.  Q descriptors never change; K / V descriptors depend on the ring stage only.
+          uint64_t dq[2][8];
+#pragma unroll
+          for (int qt = 0; qt < 2; ++qt)
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              dq[qt][kk] = umma_desc_kmajor_sw128(smem_u32(smem + Smem2::q + qt * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          uint64_t dk[8], dv[8];
+          auto make_dk = [&](int j) {
+            const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) dk[kk] = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          };
+          auto make_dv = [&](int j) {
+            const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) dv[kk] = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
+          };
+          auto issue_s = [&](int qt, int j) {   // dk must hold the descriptors of K(j)
             mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30 + qt);
             tc_fence_after();
-            const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
-            const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
-            const uint32_t d = tmem_base + qt * 128;
-#pragma unroll
-            for (int kk = 0; kk < HD / 16; ++kk) {
-              const uint32_t off = (kk >> 2) * HALF_BYTES;
-              umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S,
-                           kk != 0);
-            }
+            umma_bf16_ss_x8(tmem_base + qt * 128, dq[qt], dk, IDESC_S, 0);
             umma_commit(&bars[S_FULL + qt]);
             if (qt == 1) umma_commit(&bars[K_EMPTY + j % NK]);   // both query tiles have consumed K_j
             CE_EVT(j, 5)
           };
+          make_dk(0);
           issue_s(0, 0);
           issue_s(1, 0);
           for (int j = 0; j < n_tiles; ++j) {
+            make_dv(j);
+            if (j + 1 < n_tiles) make_dk(j + 1);
 #pragma unroll
             for (int qt = 0; qt < 2; ++qt) {
-              const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
-              const uint32_t p_tmem = tmem_base + qt * 128;
+              const uint32_t p_tmem = tmem_base + qt * 128;   // packed bf16: 8 columns per K=16 step
               const uint32_t d = tmem_base + 256 + qt * 128;
               mbar_wait(&bars[P_FULL + qt], j & 1, 40 + qt);
               if (qt == 0) mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 44);
               tc_fence_after();
-#pragma unroll
-              for (int kk = 0; kk < BKV / 32; ++kk)
-                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
+              umma_bf16_ts_x4(d, p_tmem, 8, dv[0], dv[1], dv[2], dv[3], IDESC_PV, j != 0);
               CE_EVT(j, 3)
               mbar_wait(&bars[P_FULL + 2 + qt], j & 1, 46 + qt);
               tc_fence_after();
-#pragma unroll
-              for (int kk = BKV / 32; kk < BKV / 16; ++kk)
-                umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, 1);
+              umma_bf16_ts_x4(d, p_tmem + 32, 8, dv[4], dv[5], dv[6], dv[7], IDESC_PV, 1);
               umma_commit(&bars[PV_DONE + qt]);
               if (qt == 1) umma_commit(&bars[V_EMPTY + j % NV]);   // both query tiles have consumed V_j
               CE_EVT(j, 4)

@@ -33,6 +33,7 @@ struct WeightRef {
 struct ce_dit {
   ce_dit_config cfg;
   std::map<std::string, WeightRef> w;
+  std::map<std::string, WeightRef> w32;   // fp32 validation mode: every parameter in fp32 under its reference name
   // RoPE tables, cached per latent geometry
   int rope_f = 0, rope_h = 0, rope_w = 0, rope_dev = -1;
   float* rope_cos = nullptr;
@@ -306,9 +307,35 @@ static int attention(ce_dit* h, const AttnArgs& a, cudaStream_t s) {
   return rc;
 }
 
+// ---- internals shared with dit_fp32.cu
+const float* ce_dit_internal_weight_f32(const ce_dit* h, const std::string& name, int64_t expect_numel) {
+  auto it = h->w32.find(name);
+  if (it == h->w32.end() || it->second.numel != expect_numel) return nullptr;
+  return reinterpret_cast<const float*>(it->second.ptr);
+}
+int ce_dit_internal_rope(ce_dit* h, int frames, int hp, int wp, cudaStream_t s, const float** cos_out, const float** sin_out) {
+  int rc = ensure_rope(h, frames, hp, wp, s);
+  if (rc) return rc;
+  *cos_out = h->rope_cos;
+  *sin_out = h->rope_sin;
+  return CE_OK;
+}
+const ce_dit_config* ce_dit_internal_config(const ce_dit* h) { return &h->cfg; }
+
 extern "C" {
 
 int ce_abi_version(void) { return CE_ABI_VERSION; }
+
+int ce_dit_set_weight_fp32(ce_dit* h, const char* name, const float* ptr, int64_t numel) {
+  CE_REQUIRE(h && name && ptr, "ce_dit_set_weight_fp32: null argument");
+  CE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "ce_dit_set_weight_fp32: pointer must be 16-byte aligned");
+  WeightRef r;
+  r.ptr = ptr;
+  r.dtype = 1;
+  r.numel = numel;
+  h->w32[name] = r;
+  return CE_OK;
+}
 const char* ce_last_error(void) { return ce::last_error().c_str(); }
 int ce_device_check(void) { return check_device(); }
 
@@ -577,9 +604,30 @@ int64_t ce_dit_host_staging_bytes(const ce_dit* h, int batch, int frames, int he
   return b;
 }
 
+int64_t ce_dit_host_staging_sample_offset(const ce_dit* h, int batch, int frames, int height, int width, int text_len) {
+  if (!h) return -1;
+  const ce_dit_config& c = h->cfg;
+  Bump b(nullptr);
+  b.take<bf16>((int64_t)batch * c.in_channels * frames * height * width);
+  b.take<float>(batch);
+  b.take<bf16>((int64_t)batch * text_len * c.text_dim);
+  const int64_t n_i = (int64_t)batch * 257 * c.image_dim;
+  b.take<bf16>(n_i > 0 ? n_i : 8);
+  b.off = (b.off + 255) & ~int64_t(255);
+  return b.off;
+}
+
 int ce_dit_forward_host(ce_dit* h, const void* hidden_states_host, const float* timestep_host, const void* encoder_hidden_states_host,
                         const void* encoder_hidden_states_image_host, void* sample_host, int batch, int frames, int height, int width,
                         int text_len, void* staging, int64_t staging_bytes, void* workspace, int64_t workspace_bytes, void* stream_v) {
+  return ce_dit_forward_host_ex(h, hidden_states_host, timestep_host, encoder_hidden_states_host, encoder_hidden_states_image_host, sample_host,
+                                batch, frames, height, width, text_len, staging, staging_bytes, workspace, workspace_bytes, nullptr, 0, 0, stream_v);
+}
+
+int ce_dit_forward_host_ex(ce_dit* h, const void* hidden_states_host, const float* timestep_host, const void* encoder_hidden_states_host,
+                           const void* encoder_hidden_states_image_host, void* sample_host, int batch, int frames, int height, int width,
+                           int text_len, void* staging, int64_t staging_bytes, void* workspace, int64_t workspace_bytes, void* ctx_cache,
+                           int64_t ctx_cache_bytes, int ctx_reuse, void* stream_v) {
   CE_REQUIRE(h && hidden_states_host && timestep_host && encoder_hidden_states_host && sample_host && staging, "ce_dit_forward_host: null argument");
   const ce_dit_config& c = h->cfg;
   CE_REQUIRE(staging_bytes >= ce_dit_host_staging_bytes(h, batch, frames, height, width, text_len), "ce_dit_forward_host: staging too small");
@@ -596,11 +644,12 @@ int ce_dit_forward_host(ce_dit* h, const void* hidden_states_host, const float* 
   bf16* d_o = b.take<bf16>(n_o);
   CE_CHECK_CUDA(cudaMemcpyAsync(d_x, hidden_states_host, n_x * 2, cudaMemcpyHostToDevice, s));
   CE_CHECK_CUDA(cudaMemcpyAsync(d_ts, timestep_host, batch * 4, cudaMemcpyHostToDevice, s));
+  // the encoder states are copied every call (they are part of the call's inputs); with ctx_reuse the kernels do not read them
   CE_CHECK_CUDA(cudaMemcpyAsync(d_t, encoder_hidden_states_host, n_t * 2, cudaMemcpyHostToDevice, s));
   if (encoder_hidden_states_image_host && n_i > 0)
     CE_CHECK_CUDA(cudaMemcpyAsync(d_i, encoder_hidden_states_image_host, n_i * 2, cudaMemcpyHostToDevice, s));
-  int rc = ce_dit_forward(h, d_x, d_ts, d_t, (encoder_hidden_states_image_host && n_i > 0) ? d_i : nullptr, d_o, batch, frames, height, width,
-                          text_len, workspace, workspace_bytes, nullptr, stream_v);
+  int rc = ce_dit_forward_ex(h, d_x, d_ts, d_t, (encoder_hidden_states_image_host && n_i > 0) ? d_i : nullptr, d_o, batch, frames, height, width,
+                             text_len, workspace, workspace_bytes, nullptr, ctx_cache, ctx_cache_bytes, ctx_reuse, stream_v);
   if (rc) return rc;
   CE_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_o, n_o * 2, cudaMemcpyDeviceToHost, s));
   CE_CHECK_CUDA(cudaStreamSynchronize(s));

@@ -186,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int j = 0; j < 8; ++j) y[j] += br;
             }
             if (g.out_f32) {
-              float4* o = reinterpret_cast<float4*>(g.out_f32 + (size_t)row * g.N + n);
+              float4* o = reinterpret_cast<float4*>(g.out_f32 + (size_t)row * (g.ld_f32 ? g.ld_f32 : g.N) + n);
               o[0] = make_float4(y[0], y[1], y[2], y[3]);
               o[1] = make_float4(y[4], y[5], y[6], y[7]);
               if (!g.out) continue;
@@ -268,6 +268,8 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
   CE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda, ldw must be multiples of 8 (16-byte TMA strides)");
   CE_REQUIRE((g.out != nullptr && g.ldo % 8 == 0) || (g.out == nullptr && g.out_f32 != nullptr), "gemm: out / ldo");
   CE_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
+  CE_REQUIRE(g.out_f32 == nullptr || ((reinterpret_cast<uintptr_t>(g.out_f32) & 15) == 0 && g.ld_f32 % 4 == 0 && (g.ld_f32 == 0 || g.ld_f32 >= g.N)),
+             "gemm: out_f32 must be 16-byte aligned with ld_f32 % 4 == 0, ld_f32 >= N");
   if (g.epi == EPI_BIAS_GATE_RESID || g.epi == EPI_BIAS_RESID)
     CE_REQUIRE(g.resid != nullptr && g.ldr % 8 == 0, "gemm: residual epilogue needs resid / ldr");
   if (g.epi == EPI_BIAS_GATE_RESID)

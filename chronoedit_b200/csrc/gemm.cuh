@@ -19,7 +19,8 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   bf16* out = nullptr;        // [M, ldo] bf16 (may be null when out_f32 is given)
   int ldo = 0;
-  float* out_f32 = nullptr;   // optional [M, N] fp32 copy of (acc + bias) BEFORE any rounding (parity tests)
+  float* out_f32 = nullptr;   // optional [M, ld_f32] fp32 copy of (acc + bias) BEFORE any rounding (parity tests, fp32 validation mode)
+  int ld_f32 = 0;             // leading dimension of out_f32 in elements (0 = N)
   const bf16* bias = nullptr; // [N] or null
   const bf16* bias_row = nullptr;  // [M] or null: added per output ROW (used for V^T = W_v x^T + b_v in the VAE attention)
   int epi = EPI_BIAS;

@@ -7,6 +7,8 @@
 // full barrier (both CTAs' TMA loads credit it); tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals
 // to both CTAs; the epilogue warps of both CTAs release the accumulator stage on the leader's barrier.
 // Same epilogues, tile rasterisation and launch interface as gemm.cu (which remains the path for small problems).
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace ce {
@@ -38,6 +40,10 @@ __device__ __forceinline__ float gelu_tanh_f2(float x) {
 }
 __device__ __forceinline__ float gelu_erf_f2(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 
+// ELECT: the single producer / issuer lane is chosen with elect.sync instead of `lane == 0` -- under elect.sync the compiler knows
+// the region runs in one thread and feeds the uniform-register operands of UTMALDG / UTCHMMA directly; under `lane == 0` it wraps
+// every such instruction in a serialisation loop (ELECT / BRA.U.ANY), ~10 extra instructions per MMA (A/B: CE_GEMM_ELECT=0).
+template <bool ELECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmArgs g) {
   constexpr uint32_t IDESC = umma_idesc_bf16(2 * BM, BN, 0);
@@ -86,7 +92,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane in EACH CTA)
-    if (lane == 0) {
+    if (ELECT ? elect_one_sync() : lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -109,7 +115,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    if (leader && (ELECT ? elect_one_sync() : lane == 0)) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -179,7 +185,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
               for (int j = 0; j < 8; ++j) y[j] += br;
             }
             if (g.out_f32) {
-              float4* o = reinterpret_cast<float4*>(g.out_f32 + (size_t)row * g.N + n);
+              float4* o = reinterpret_cast<float4*>(g.out_f32 + (size_t)row * (g.ld_f32 ? g.ld_f32 : g.N) + n);
               o[0] = make_float4(y[0], y[1], y[2], y[3]);
               o[1] = make_float4(y[4], y[5], y[6], y[7]);
               if (!g.out) continue;
@@ -234,11 +240,20 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 
 int launch_gemm_bf16_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
-  CE_ENSURE_SMEM(gemm_bf16_2cta_kernel, smem);
+  static const bool elect = [] {
+    const char* e = getenv("CE_GEMM_ELECT");
+    return !(e && e[0] == '0');
+  }();
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + BN - 1) / BN);
   int clusters = device_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_2cta_kernel<<<2 * clusters, THREADS, smem, stream>>>(ta, tb, g);
+  if (elect) {
+    CE_ENSURE_SMEM(gemm_bf16_2cta_kernel<true>, smem);
+    gemm_bf16_2cta_kernel<true><<<2 * clusters, THREADS, smem, stream>>>(ta, tb, g);
+  } else {
+    CE_ENSURE_SMEM(gemm_bf16_2cta_kernel<false>, smem);
+    gemm_bf16_2cta_kernel<false><<<2 * clusters, THREADS, smem, stream>>>(ta, tb, g);
+  }
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -17,6 +17,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// One lane of a converged warp (elect.sync): code under `if (elect_one_sync())` is known to the compiler to run in exactly one
+// thread, so warp-uniform operands (tcgen05 descriptors, TMEM addresses) go to uniform registers without a serialisation loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -161,6 +173,44 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Eight / four MMAs in ONE asm statement: nothing but the UTCHMMA instructions themselves between consecutive issues.  The
+// issuing thread's own work between two tcgen05.mma (descriptor arithmetic, predicate set-up) is NOT hidden behind the previous
+// MMA when that work is longer than the MMA itself (64 cycles at M128 x N128 x K16): measured in the attention kernel, 95-115
+// cycles per MMA with the descriptors computed inline vs the 64-cycle floor (profiles/r2d_attention_per_mma_issue_stamps.log).
+// The first MMA overwrites D when acc_first == 0, the others accumulate.
+__device__ __forceinline__ void umma_bf16_ss_x8(uint32_t tmem_d, const uint64_t (&da)[8], const uint64_t (&db)[8], uint32_t idesc,
+                                                uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %18, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %9, %17, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %10, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %11, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %12, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %13, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %14, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %7, %15, %17, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %8, %16, %17, q;\n\t}" ::"r"(tmem_d),
+      "l"(da[0]), "l"(da[1]), "l"(da[2]), "l"(da[3]), "l"(da[4]), "l"(da[5]), "l"(da[6]), "l"(da[7]), "l"(db[0]), "l"(db[1]), "l"(db[2]),
+      "l"(db[3]), "l"(db[4]), "l"(db[5]), "l"(db[6]), "l"(db[7]), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+// A from TMEM at tmem_a, tmem_a + a_step, ... (packed bf16 columns), B descriptors db[0..3]
+__device__ __forceinline__ void umma_bf16_ts_x4(uint32_t tmem_d, uint32_t tmem_a, uint32_t a_step, uint64_t db0, uint64_t db1, uint64_t db2,
+                                                uint64_t db3, uint32_t idesc, uint32_t acc_first) {
+  const uint32_t a1 = tmem_a + a_step, a2 = tmem_a + 2 * a_step, a3 = tmem_a + 3 * a_step;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %5, %9, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %6, %9, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], %7, %9, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%4], %8, %9, q;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(a1), "r"(a2), "r"(a3), "l"(db0), "l"(db1), "l"(db2), "l"(db3), "r"(idesc), "r"(acc_first)
       : "memory");
 }
 // Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.

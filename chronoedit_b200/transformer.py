@@ -397,9 +397,11 @@ class ChronoEditTransformer3DModel(nn.Module):
 
     @torch.no_grad()
     def forward_host(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
-                     encoder_hidden_states_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     encoder_hidden_states_image: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                     return_device_sample: bool = False):
         """End-to-end variant: all tensors are (pinned) HOST bf16/fp32 tensors; H2D, forward and D2H happen inside the
-        C-ABI call (ce_dit_forward_host).  Returns the host sample tensor."""
+        C-ABI call (ce_dit_forward_host_ex).  Returns the host sample tensor (and, with `return_device_sample`, a view of the same
+        sample still on the device -- valid until the next forward_host call -- for the scheduler step)."""
         if not self._packed:
             self.pack_weights()
         B, C, T, H, W = hidden_states.shape
@@ -417,11 +419,20 @@ class ChronoEditTransformer3DModel(nn.Module):
             self._workspaces["staging"] = st
         if out is None:
             out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16).pin_memory()
+        ctx_buf, ctx_reuse = (None, 0)
+        if self.cache_context:
+            ctx_buf, ctx_reuse = self._context_slot(encoder_hidden_states, encoder_hidden_states_image, encoder_hidden_states,
+                                                    encoder_hidden_states_image)
         with torch.cuda.device(self.device):
-            check(L.ce_dit_forward_host(self._handle, ptr(hidden_states), ptr(t), ptr(encoder_hidden_states),
-                                        ptr(encoder_hidden_states_image), ptr(out), B, T, H, W, Lt, ptr(st), st.numel(), ptr(ws),
-                                        ws.numel(), current_stream()))
-        return out
+            check(L.ce_dit_forward_host_ex(self._handle, ptr(hidden_states), ptr(t), ptr(encoder_hidden_states),
+                                           ptr(encoder_hidden_states_image), ptr(out), B, T, H, W, Lt, ptr(st), st.numel(), ptr(ws),
+                                           ws.numel(), ptr(ctx_buf), ctx_buf.numel() if ctx_buf is not None else 0, ctx_reuse,
+                                           current_stream()))
+        if not return_device_sample:
+            return out
+        off = L.ce_dit_host_staging_sample_offset(self._handle, B, T, H, W, Lt)
+        dev_sample = st[off: off + out.numel() * 2].view(torch.bfloat16).view(out.shape)
+        return out, dev_sample
 
     def launches_per_forward(self) -> int:
         return int(_lib.lib().ce_dit_last_launch_count(self._handle)) if self._handle else 0

@@ -110,6 +110,28 @@ int ce_dit_forward_host(ce_dit* h, const void* hidden_states_host, const float* 
                         void* sample_host, int batch, int frames, int height, int width, int text_len, void* staging,
                         int64_t staging_bytes, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The host-buffer call with the step-invariant context cache of ce_dit_forward_ex (device buffer, caller-owned).  The sample also
+ * stays in `staging` at byte offset ce_dit_host_staging_sample_offset(...) (bf16 [B, out_channels, frames, height, width]) until
+ * the next call, so that the scheduler step can consume it on the device without a second copy. */
+int ce_dit_forward_host_ex(ce_dit* h, const void* hidden_states_host, const float* timestep_host,
+                           const void* encoder_hidden_states_host, const void* encoder_hidden_states_image_host,
+                           void* sample_host, int batch, int frames, int height, int width, int text_len, void* staging,
+                           int64_t staging_bytes, void* workspace, int64_t workspace_bytes, void* ctx_cache,
+                           int64_t ctx_cache_bytes, int ctx_reuse, void* stream);
+int64_t ce_dit_host_staging_sample_offset(const ce_dit* h, int batch, int frames, int height, int width, int text_len);
+
+/* VALIDATION mode: the same forward in fp32 -- fp32 inputs, fp32 parameters (registered under their REFERENCE names, unfused:
+ * blocks.N.attn1.to_q.weight ..., blocks.N.scale_shift_table [6*D], scale_shift_table [2*D], patch_embedding.weight [D, Cin*4]),
+ * fp32 residual stream, fp32 outputs.  Matrix products run on the same tcgen05 GEMM with every fp32 operand split into two bf16
+ * terms (A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, fp32 accumulate; csrc/dit_fp32.cu).  It exists so that north_star's
+ * rtol 1e-3 / atol 1e-4 can be asserted end to end against the reference's fp32 run (tests/test_gpu_fp32_mode.py); it is about
+ * 5-10x slower than the bf16 path and is not what bench.py measures.  block_out: optional, block 0's output [B*L, D] fp32. */
+int ce_dit_set_weight_fp32(ce_dit* h, const char* name, const float* ptr, int64_t numel);
+int64_t ce_dit_fp32_workspace_bytes(const ce_dit* h, int batch, int frames, int height, int width, int text_len);
+int ce_dit_forward_fp32(ce_dit* h, const float* hidden_states, const float* timestep, const float* encoder_hidden_states,
+                        const float* encoder_hidden_states_image, float* sample, int batch, int frames, int height, int width,
+                        int text_len, void* workspace, int64_t workspace_bytes, float* block_out, void* stream);
+
 /* Kernel launches issued by the last ce_dit_forward on this handle (bench.py's "gpu_launches"). */
 int64_t ce_dit_last_launch_count(const ce_dit* h);
 

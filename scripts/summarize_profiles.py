@@ -41,3 +41,35 @@ for k in ("gemm", "attn", "xattn", "rows", "conv"):
         for r in rows[2:]:
             f.write(",".join('"' + r[hdr.index(c)].replace('"', "'")[:90] + '"' for c in cols) + "\n")
     print(f"profiles/{tag}_ncu_{k}.csv written ({len(rows)-2} launches)")
+
+# 3. profiles/traffic.json: per-launch DRAM traffic of the dominant kernel classes (what bench.py's roofline.*.traffic reads),
+#    taken from the newest profiles/*_ncu_<class>.csv that exists; algorithmic bytes = the launch's operands touched once.
+def _first_row(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd = float(r[hdr.index("dram__bytes_read.sum")]) * scale[units[hdr.index("dram__bytes_read.sum")]]
+    wr = float(r[hdr.index("dram__bytes_write.sum")]) * scale[units[hdr.index("dram__bytes_write.sum")]]
+    return r[0], rd, wr, float(r[hdr.index("gpu__time_duration.sum")])
+
+def _newest(kind):
+    import glob
+    c = sorted(glob.glob(f"profiles/*_ncu_{kind}.csv"), key=os.path.getmtime)
+    return c[-1] if c else None
+
+LAUNCH = {  # the launch each capture script profiles (scripts/gpu_profile.sh -> scripts/bench_ops.py) and its algorithmic bytes
+    "gemm": ("gemm", "QKV GEMM M=14400 N=15360 K=5120 (bf16 A, W, out)", (14400 * 5120 + 15360 * 5120 + 14400 * 15360) * 2),
+    "attention": ("attn", "self-attention B=2 H=40 L=7200 hd=128 (q, k, v, out once)", 4 * 2 * 7200 * 5120 * 2),
+    "conv": ("conv", "conv 3x3x3 96->96 on 4x720x1280 (input 6 frames incl. causal history + output 4 frames, bf16)", (6 + 4) * 720 * 1280 * 96 * 2),
+}
+traffic = {}
+for name, (kind, desc, alg) in LAUNCH.items():
+    pth = _newest(kind)
+    if not pth:
+        continue
+    kname, rd, wr, ms = _first_row(pth)
+    traffic[name] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": kname[:80], "launch": f"{desc} ({pth})",
+                     "algorithmic_bytes": alg, "ratio": round((rd + wr) / alg, 3), "ncu_ms": ms}
+with open("profiles/traffic.json", "w") as f:
+    json.dump(traffic, f, indent=1)
+print(json.dumps(traffic, indent=1))
