@@ -93,7 +93,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(&bars[Q_FULL], TILE_BYTES);
       tma_load_3d(smem + SmemLayout::q, &tma_q, &bars[Q_FULL], h * HD, q0, b);
       tma_load_3d(smem + SmemLayout::q + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0, b);
@@ -142,36 +142,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (one elected lane; every descriptor is fixed
+    // per group -- one K, V and P buffer each -- so all of them are built once and the MMAs go out eight per asm statement)
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major) x K^T (K-major)
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (K-major) x V (MN-major)
-      const uint32_t q_addr = smem_u32(smem + SmemLayout::q);
+      uint64_t dq[8], dkk[2][8], dp[2][8], dvv[2][8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        dq[kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::q) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          dkk[g][kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::k + g * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          dp[g][kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::p + g * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+          dvv[g][kk] = umma_desc_mnmajor_sw128(smem_u32(smem + SmemLayout::v + g * TILE_BYTES) + kk * 2048, HALF_BYTES);
+        }
+      }
       auto issue_s = [&](int g, int t) {
         mbar_wait(&bars[K_FULL + g], t & 1, 30 + g);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + SmemLayout::k + g * TILE_BYTES);
-        const uint32_t d = tmem_base + g * 128;
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * HALF_BYTES;
-          umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3),
-                       umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3), IDESC_S, kk != 0);
-        }
+        umma_bf16_ss_x8(tmem_base + g * 128, dq, dkk[g], IDESC_S, 0);
         umma_commit(&bars[K_EMPTY + g]);
         umma_commit(&bars[S_FULL + g]);
       };
       auto issue_pv = [&](int g, int t) {
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + SmemLayout::p + g * TILE_BYTES);
-        const uint32_t v_addr = smem_u32(smem + SmemLayout::v + g * TILE_BYTES);
-        const uint32_t d = tmem_base + 256 + g * 128;
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
-          umma_bf16_ss(d, da, db, IDESC_PV, (t | kk) != 0);
-        }
+        umma_bf16_ss_x8(tmem_base + 256 + g * 128, dp[g], dvv[g], IDESC_PV, t != 0);
         umma_commit(&bars[V_EMPTY + g]);
         umma_commit(&bars[PV_DONE + g]);
       };

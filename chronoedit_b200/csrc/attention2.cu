@@ -91,7 +91,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (event-driven)
       if (lane == 0) {

@@ -77,7 +77,7 @@ conv3d_cl_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {  // one lane, known to the compiler as such: no per-instruction serialisation loops around UTMALDG / UTCHMMA
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
@@ -103,7 +103,7 @@ conv3d_cl_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {  // one lane, known to the compiler as such: no per-instruction serialisation loops around UTMALDG / UTCHMMA
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -117,8 +117,7 @@ conv3d_cl_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
           tc_fence_after();
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+umma_bf16_ss_x4(d_tmem, da, db, IDESC, kb != 0);   // the four K16 steps of the k-block, one asm statement
           umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;

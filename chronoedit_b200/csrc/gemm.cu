@@ -92,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {  // one lane, known to the compiler as such: no per-instruction serialisation loops around UTMALDG / UTCHMMA
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -112,7 +112,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {  // one lane, known to the compiler as such: no per-instruction serialisation loops around UTMALDG / UTCHMMA
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -126,11 +126,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tc_fence_after();
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle row: start-address field += 2
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
-          }
+          // four K16 steps (+32 bytes each inside the 128-byte swizzle row: start-address field += 2), one asm statement
+          umma_bf16_ss_x4(d_tmem, da, db, IDESC, kb != 0);
           umma_commit(&empty[stage]);  // slot reusable once these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;

@@ -129,8 +129,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           tc_fence_after();
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+          if (ELECT) {
+            umma_bf16_ss_2sm_x4(d_tmem, da, db, IDESC, kb != 0);   // the four K16 steps of the k-block, one asm statement
+          } else {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+          }
           umma_commit_2sm(&empty[stage], 3);  // both CTAs' producers
           if (++stage == STAGES) {
             stage = 0;

@@ -198,6 +198,35 @@ __device__ __forceinline__ void umma_bf16_ss_x8(uint32_t tmem_d, const uint64_t 
       "l"(db[3]), "l"(db[4]), "l"(db[5]), "l"(db[6]), "l"(db[7]), "r"(idesc), "r"(acc_first)
       : "memory");
 }
+// Four K16 steps of one 64-wide k-block: descriptors base + 2*k (32 bytes along K inside the 128-byte swizzle row)
+__device__ __forceinline__ void umma_bf16_ss_x4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm_x4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, q;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
 // A from TMEM at tmem_a, tmem_a + a_step, ... (packed bf16 columns), B descriptors db[0..3]
 __device__ __forceinline__ void umma_bf16_ts_x4(uint32_t tmem_d, uint32_t tmem_a, uint32_t a_step, uint64_t db0, uint64_t db1, uint64_t db2,
                                                 uint64_t db3, uint32_t idesc, uint32_t acc_first) {

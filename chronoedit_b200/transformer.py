@@ -216,6 +216,66 @@ class ChronoEditTransformer3DModel(nn.Module):
             c.num_layers, c.image_dim or 0, c.added_kv_proj_dim or 0, c.rope_max_seq_len, c.rope_temporal_skip_len, c.eps,
             *c.patch_size)
 
+    def _ensure_handle(self):
+        if self._handle is None:
+            h = _lib.c_void_p()
+            cfg = self._cfg_c()
+            check(_lib.lib().ce_dit_create(_lib.ctypes.byref(cfg), _lib.ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    # ------------------------------------------------------------------------------------------ fp32 validation mode
+    @torch.no_grad()
+    def enable_fp32_validation(self, state_dict_fp32: Dict[str, torch.Tensor]) -> None:
+        """Register an fp32 copy of every parameter (reference names, e.g. the reference model's own fp32 state dict) for
+        `forward_fp32`.  The bf16 parameters of this module are untouched."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise CEError("fp32 validation mode needs the module on a CUDA (sm_100) device; there is no CPU path")
+        L = _lib.lib()
+        self._ensure_handle()
+        own = {n for n, _ in self.named_parameters()}
+        missing = sorted(own - set(state_dict_fp32))
+        if missing:
+            raise CEError(f"enable_fp32_validation: state dict lacks {len(missing)} parameters, first: {missing[0]}")
+        keep = {}
+        for n in own:
+            t = state_dict_fp32[n].detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep[n] = t
+            check(L.ce_dit_set_weight_fp32(self._handle, n.encode(), ptr(t), t.numel()))
+        self._fp32_keepalive = keep
+
+    @torch.no_grad()
+    def forward_fp32(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                     encoder_hidden_states_image: Optional[torch.Tensor] = None, return_block0: bool = False):
+        """VALIDATION mode (include/chronoedit_b200.h, ce_dit_forward_fp32): fp32 in, fp32 weights, fp32 out, every matrix product
+        on the tcgen05 GEMM with split-bf16 operands.  Meets rtol 1e-3 / atol 1e-4 against the reference's fp32 run end to end
+        (tests/test_gpu_fp32_mode.py); far slower than forward() and not part of any benchmark."""
+        if not getattr(self, "_fp32_keepalive", None):
+            raise CEError("call enable_fp32_validation(fp32_state_dict) first")
+        dev = self.device
+        B, C, T, H, W = hidden_states.shape
+        x = hidden_states.to(device=dev, dtype=torch.float32).contiguous()
+        t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        t = (t.expand(B) if t.numel() == 1 and B > 1 else t).contiguous()
+        txt = encoder_hidden_states.to(device=dev, dtype=torch.float32).contiguous()
+        img = None if encoder_hidden_states_image is None else encoder_hidden_states_image.to(device=dev, dtype=torch.float32).contiguous()
+        L = _lib.lib()
+        Lt = txt.shape[1]
+        n = L.ce_dit_fp32_workspace_bytes(self._handle, B, T, H, W, Lt)
+        if n < 0:
+            raise CEError("fp32 validation mode: unsupported geometry")
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.float32, device=dev)
+        b0 = None
+        if return_block0:
+            b0 = torch.empty(B * T * (H // 2) * (W // 2), self.config.num_attention_heads * self.config.attention_head_dim,
+                             dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.ce_dit_forward_fp32(self._handle, ptr(x), ptr(t), ptr(txt), ptr(img), ptr(out), B, T, H, W, Lt, ptr(ws), ws.numel(),
+                                        ptr(b0), current_stream()))
+        return (out, b0) if return_block0 else out
+
     @torch.no_grad()
     def pack_weights(self) -> None:
         """Build the fused buffers the kernels read (QKV / KV rows stacked, scale_shift_tables stacked) and register
@@ -230,11 +290,7 @@ class ChronoEditTransformer3DModel(nn.Module):
             want = torch.float32 if any(k in n for k in KEEP_FP32) else torch.bfloat16
             if p.dtype != want:
                 p.data = p.data.to(want)
-        if self._handle is None:
-            h = _lib.c_void_p()
-            cfg = self._cfg_c()
-            check(L.ce_dit_create(_lib.ctypes.byref(cfg), _lib.ctypes.byref(h)))
-            self._handle = h
+        self._ensure_handle()
         keep: Dict[str, torch.Tensor] = {}
 
         def fuse(prefix, holders, attr):

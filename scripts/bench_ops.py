@@ -164,6 +164,10 @@ if __name__ == "__main__":
     if "attnself" in what:
         bench_attn()
         bench_attn(B=1, Lq=28800, Lk=28800, nbuf=2)
+    if "attncross" in what:
+        bench_attn(Lk=512)
+        bench_attn(Lk=257)
+        bench_attn_dual()
     if "attnlib" in what:
         bench_attn()
         bench_attn_libs()
