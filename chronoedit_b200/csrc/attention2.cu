@@ -33,6 +33,12 @@ constexpr uint32_t TILE_BYTES = 128 * 128 * 2;
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
+// defaults of the A/B knobs (chosen from profiles/r2*_attention_*.log)
+#define CE_ATTN_POLY_DEFAULT 0
+#define CE_ATTN_SPEC_DEFAULT false
+#define CE_ATTN_SPIN_DEFAULT false
+#define CE_ATTN_QUARTERS_DEFAULT false
+
 struct Smem2 {
   static constexpr uint32_t q = 0;                         // 2 tiles
   static constexpr uint32_t k = q + 2 * TILE_BYTES;        // NK tiles
@@ -42,29 +48,31 @@ struct Smem2 {
 };
 
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_EMPTY = V_FULL + NV, S_FULL = V_EMPTY + NV,
-       P_FULL = S_FULL + 2 /* [half*2 + q]: keys 0-63 / 64-127 of the tile */, PV_DONE = P_FULL + 4, NUM_BARS2 = PV_DONE + 2 };
+       P_FULL = S_FULL + 2 /* [part*2 + q]: part = 32-key quarter (QUARTERS) or 64-key half of the tile */, PV_DONE = P_FULL + 8,
+       NUM_BARS2 = PV_DONE + 2 };
 
-// POLY8 of every 8 exp2 pairs are evaluated on the FMA pipe (f2_exp2_poly), the rest on the MUFU.
-// SPEC: from the second key tile on, the exponentials of a tile start against the running maximum of the PREVIOUS tiles as
-// soon as the first 32 score columns have arrived from TMEM, while the other 96 columns are still in flight and the tile's own
-// row maximum is folded in between the MUFU instructions; only when that maximum turns out to exceed the running one by more
-// than the lazy-rescale threshold (rare after the first tiles) is the tile redone the classic way (max first).  Results are
-// bit-identical to the non-speculative order: when no rescale is due the classic path uses the same stale maximum.
-// FIXED: the MMA issuer walks a FIXED order with blocking waits -- per key tile j: P.V_0(j) first half, second half, S_0(j+1),
-// then the same three for query tile 1 -- instead of issuing whatever is ready.  The tensor pipe executes in issue order, so a
-// greedy issuer lets the other tile's ready-but-not-urgent MMAs (its P.V first half) slip in front of the one chain that
-// bounds the loop (P second half -> P.V second half -> next S -> softmax): measured with the event log below, the greedy order
-// settles at ~3600 cycles per key tile per query tile, while this chain alone is ~2770 (230 S-ready latency + 1770 softmax +
-// 256 + 512 MMA) and the other tile's three MMAs fit in its softmax phase.  With the fixed order the two tiles fall into that
-// anti-phase schedule by themselves.  The producer likewise loads K(j), V(j) in order with blocking waits (no polling warps
-// competing with the softmax warps for issue slots).
-template <int POLY8, bool SPEC, bool FIXED>
+// The MMA issuer (one elected lane of warp 1) walks a FIXED order with the descriptors computed ahead of its waits and every
+// group of MMAs issued as ONE asm statement: per key tile j, for query tile 0 then 1: P.V(j) part by part as the softmax
+// publishes P, then S(j+1).  Why (profiles/r2c_*, r2d_*, r2f_*): (i) the issuing thread's own work between two tcgen05.mma is
+// not hidden when it is longer than the MMA (64 cycles here): with inline descriptor arithmetic and the compiler's per-MMA
+// serialisation loop (`if (lane == 0)` instead of elect.sync) each MMA took 95-115 cycles; (ii) the tensor pipe executes in
+// issue order, so a greedy "issue whatever is ready" loop lets one tile's early P.V slip in front of the other tile's S.
+// Template knobs (A/B through the environment, see launch_attention2):
+//   POLY8    of every 8 exp2 pairs are evaluated on the FMA pipe (f2_exp2_poly), the rest on the MUFU;
+//   SPEC     exponentials start against the PREVIOUS running maximum on the first 32 score columns while the other 96 are still
+//            coming from TMEM, the tile's own maximum is folded in between the MUFU instructions, and the tile is redone the
+//            classic way (max first) only when that maximum exceeds the running one by more than the lazy-rescale threshold --
+//            bit-identical results, because without a rescale the classic path uses the same stale maximum;
+//   SPIN     the waits on the critical chain (issuer: P published; softmax: S ready) spin on test_wait instead of suspending;
+//   QUARTERS P is published (and P.V issued) in four 32-key parts instead of two 64-key halves.
+template <int POLY8, bool SPEC, bool SPIN, bool QUARTERS>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem2::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS2);
+  constexpr int PARTS = QUARTERS ? 4 : 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,7 +86,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       printf("[chronoedit_b200] attention2: dynamic shared memory not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < NUM_BARS2; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 4) ? 128 : 1);
+    for (int i = 0; i < NUM_BARS2; ++i) mbar_init(&bars[i], (i >= P_FULL && i < P_FULL + 8) ? 128 : 1);
     fence_mbar_init();
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -89,214 +97,99 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool timed_blk = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer (event-driven)
-      if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer: K(t), V(t) in order, blocking waits
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&bars[Q_FULL], 2 * TILE_BYTES);
 #pragma unroll
         for (int qt = 0; qt < 2; ++qt) {
           tma_load_3d(smem + Smem2::q + qt * TILE_BYTES, &tma_q, &bars[Q_FULL], h * HD, q0 + qt * BQ, b);
           tma_load_3d(smem + Smem2::q + qt * TILE_BYTES + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0 + qt * BQ, b);
         }
-        int k_next = 0, v_next = 0;
-        uint64_t t_start = 0;
-        uint32_t idle = 0;
-        if (FIXED) {
-          for (int t = 0; t < n_tiles; ++t) {
-            {
-              const int st = t % NK;
-              mbar_wait(&bars[K_EMPTY + st], ((t / NK) & 1) ^ 1, 10 + st);
-              uint8_t* ks = smem + Smem2::k + st * TILE_BYTES;
-              mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
-              tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, t * BKV, b);
-              tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, t * BKV, b);
-            }
-            {
-              const int st = t % NV;
-              mbar_wait(&bars[V_EMPTY + st], ((t / NV) & 1) ^ 1, 20 + st);
-              uint8_t* vs = smem + Smem2::v + st * TILE_BYTES;
-              mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
-              tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, t * BKV, b);
-              tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, t * BKV, b);
-            }
+        for (int t = 0; t < n_tiles; ++t) {
+          {
+            const int st = t % NK;
+            mbar_wait(&bars[K_EMPTY + st], ((t / NK) & 1) ^ 1, 10 + st);
+            uint8_t* ks = smem + Smem2::k + st * TILE_BYTES;
+            mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
+            tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, t * BKV, b);
+            tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, t * BKV, b);
           }
-          k_next = v_next = n_tiles;
-        }
-        while (k_next < n_tiles || v_next < n_tiles) {
-          bool progress = false;
-          if (k_next < n_tiles) {
-            const int st = k_next % NK;
-            if (mbar_test_wait(&bars[K_EMPTY + st], ((k_next / NK) & 1) ^ 1)) {
-              uint8_t* ks = smem + Smem2::k + st * TILE_BYTES;
-              mbar_arrive_expect_tx(&bars[K_FULL + st], TILE_BYTES);
-              tma_load_3d(ks, &tma_k, &bars[K_FULL + st], h * HD, k_next * BKV, b);
-              tma_load_3d(ks + HALF_BYTES, &tma_k, &bars[K_FULL + st], h * HD + 64, k_next * BKV, b);
-              ++k_next;
-              progress = true;
-            }
-          }
-          if (v_next < n_tiles) {
-            const int st = v_next % NV;
-            if (mbar_test_wait(&bars[V_EMPTY + st], ((v_next / NV) & 1) ^ 1)) {
-              uint8_t* vs = smem + Smem2::v + st * TILE_BYTES;
-              mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
-              tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, v_next * BKV, b);
-              tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, v_next * BKV, b);
-              ++v_next;
-              progress = true;
-            }
-          }
-          if (progress) {
-            idle = 0;
-          } else if ((++idle & 0xFFF) == 0) {
-            if (t_start == 0) t_start = global_timer_ns();
-            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
-              printf("[chronoedit_b200] attention2 producer stalled: block=(%d,%d,%d) k=%d v=%d\n", blockIdx.x, blockIdx.y, blockIdx.z, k_next, v_next);
-              __trap();
-            }
+          {
+            const int st = t % NV;
+            mbar_wait(&bars[V_EMPTY + st], ((t / NV) & 1) ^ 1, 20 + st);
+            uint8_t* vs = smem + Smem2::v + st * TILE_BYTES;
+            mbar_arrive_expect_tx(&bars[V_FULL + st], TILE_BYTES);
+            tma_load_3d(vs, &tma_v, &bars[V_FULL + st], h * HD, t * BKV, b);
+            tma_load_3d(vs + HALF_BYTES, &tma_v, &bars[V_FULL + st], h * HD + 64, t * BKV, b);
           }
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer (one elected lane)
+      // ---------------------------------------------------------------- MMA issuer (one elected lane, fixed order)
       if (elect_one_sync()) {
         constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major, smem) x K^T (K-major, smem)
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (TMEM) x V (MN-major, smem)
         mbar_wait(&bars[Q_FULL], 0, 1);
-        int s_next[2] = {0, 0}, pv_next[2] = {0, 0}, pv_half[2] = {0, 0};
-        const bool timed_i = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-#define CE_EVT(jj, slot)                                                             \
-  if (timed_i && (jj) >= 16 && (jj) < 24) a.timing[64 + qt * 64 + ((jj)-16) * 8 + (slot)] = clock64();
-        uint64_t t_start = 0;
-        uint32_t idle = 0;
-        if (FIXED) {
-          // descriptors are computed AHEAD of the waits (the waits are slack time); the issue itself is one asm statement per
-          // group of MMAs.  Q descriptors never change; K / V descriptors depend on the ring stage only.
-          uint64_t dq[2][8];
+#define CE_EVT(jj, slot) \
+  if (timed_blk && (jj) >= 16 && (jj) < 24) a.timing[64 + qt * 64 + ((jj)-16) * 8 + (slot)] = clock64();
+        // descriptors are computed AHEAD of the waits (slack time); Q descriptors never change, K / V ones depend on the ring stage
+        uint64_t dq[2][8];
 #pragma unroll
-          for (int qt = 0; qt < 2; ++qt)
+        for (int qt = 0; qt < 2; ++qt)
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              dq[qt][kk] = umma_desc_kmajor_sw128(smem_u32(smem + Smem2::q + qt * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          uint64_t dk[8], dv[8];
-          auto make_dk = [&](int j) {
-            const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
+          for (int kk = 0; kk < 8; ++kk)
+            dq[qt][kk] = umma_desc_kmajor_sw128(smem_u32(smem + Smem2::q + qt * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+        uint64_t dk[8], dv[8];
+        auto make_dk = [&](int j) {
+          const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) dk[kk] = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          };
-          auto make_dv = [&](int j) {
-            const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
+          for (int kk = 0; kk < 8; ++kk) dk[kk] = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
+        };
+        auto make_dv = [&](int j) {
+          const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) dv[kk] = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
-          };
-          auto issue_s = [&](int qt, int j) {   // dk must hold the descriptors of K(j)
-            mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30 + qt);
-            tc_fence_after();
-            umma_bf16_ss_x8(tmem_base + qt * 128, dq[qt], dk, IDESC_S, 0);
-            umma_commit(&bars[S_FULL + qt]);
-            if (qt == 1) umma_commit(&bars[K_EMPTY + j % NK]);   // both query tiles have consumed K_j
-            CE_EVT(j, 5)
-          };
-          make_dk(0);
-          issue_s(0, 0);
-          issue_s(1, 0);
-          for (int j = 0; j < n_tiles; ++j) {
-            make_dv(j);
-            if (j + 1 < n_tiles) make_dk(j + 1);
-#pragma unroll
-            for (int qt = 0; qt < 2; ++qt) {
-              const uint32_t p_tmem = tmem_base + qt * 128;   // packed bf16: 8 columns per K=16 step
-              const uint32_t d = tmem_base + 256 + qt * 128;
-              mbar_wait(&bars[P_FULL + qt], j & 1, 40 + qt);
-              if (qt == 0) mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 44);
-              tc_fence_after();
-              umma_bf16_ts_x4(d, p_tmem, 8, dv[0], dv[1], dv[2], dv[3], IDESC_PV, j != 0);
-              CE_EVT(j, 3)
-              mbar_wait(&bars[P_FULL + 2 + qt], j & 1, 46 + qt);
-              tc_fence_after();
-              umma_bf16_ts_x4(d, p_tmem + 32, 8, dv[4], dv[5], dv[6], dv[7], IDESC_PV, 1);
-              umma_commit(&bars[PV_DONE + qt]);
-              if (qt == 1) umma_commit(&bars[V_EMPTY + j % NV]);   // both query tiles have consumed V_j
-              CE_EVT(j, 4)
-              if (j + 1 < n_tiles) issue_s(qt, j + 1);
-            }
-          }
-          pv_next[0] = pv_next[1] = n_tiles;
-        }
-        while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
-          bool progress = false;
+          for (int kk = 0; kk < 8; ++kk) dv[kk] = umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES);
+        };
+        auto issue_s = [&](int qt, int j) {   // dk must hold the descriptors of K(j)
+          mbar_wait(&bars[K_FULL + j % NK], (j / NK) & 1, 30 + qt);
+          tc_fence_after();
+          umma_bf16_ss_x8(tmem_base + qt * 128, dq[qt], dk, IDESC_S, 0);
+          umma_commit(&bars[S_FULL + qt]);
+          if (qt == 1) umma_commit(&bars[K_EMPTY + j % NK]);   // both query tiles have consumed K_j
+          CE_EVT(j, 5)
+        };
+        make_dk(0);
+        issue_s(0, 0);
+        issue_s(1, 0);
+        for (int j = 0; j < n_tiles; ++j) {
+          make_dv(j);
+          if (j + 1 < n_tiles) make_dk(j + 1);
 #pragma unroll
           for (int qt = 0; qt < 2; ++qt) {
-            // S_qt(j) needs K_j.  It overwrites the S|P region that P.V_qt(j-1) reads, which is safe as soon as that MMA has
-            // been ISSUED (tcgen05.mma instructions of one thread execute in issue order).  Issue order matters: P.V_qt(j) is
-            // followed IMMEDIATELY by S_qt(j+1), so that the two query tiles get their next S a full 1024 cycles apart and
-            // their softmax (MUFU) phases fall into anti-phase instead of running in lockstep.
-            auto try_s = [&]() {
-              const int j = s_next[qt];
-              if (j < n_tiles && pv_next[qt] >= j && mbar_test_wait(&bars[K_FULL + j % NK], (j / NK) & 1)) {
-                tc_fence_after();
-                const uint32_t q_addr = smem_u32(smem + Smem2::q + qt * TILE_BYTES);
-                const uint32_t k_addr = smem_u32(smem + Smem2::k + (j % NK) * TILE_BYTES);
-                const uint32_t d = tmem_base + qt * 128;
+            const uint32_t p_tmem = tmem_base + qt * 128;   // packed bf16: 8 columns per K=16 step
+            const uint32_t d = tmem_base + 256 + qt * 128;
 #pragma unroll
-                for (int kk = 0; kk < HD / 16; ++kk) {
-                  const uint32_t off = (kk >> 2) * HALF_BYTES;
-                  umma_bf16_ss(d, umma_desc_kmajor_sw128(q_addr + off) + 2 * (kk & 3), umma_desc_kmajor_sw128(k_addr + off) + 2 * (kk & 3),
-                               IDESC_S, kk != 0);
-                }
-                umma_commit(&bars[S_FULL + qt]);
-                CE_EVT(j, 5)
-                ++s_next[qt];
-                if (s_next[qt ^ 1] > j) umma_commit(&bars[K_EMPTY + j % NK]);  // both query tiles have consumed K_j
-                progress = true;
-              }
-            };
-            try_s();
-            // P.V_qt(j) in two K halves: keys 0-63 as soon as the group has published the first half of P (it is still
-            // exponentiating the second half), keys 64-127 when the rest is there.  Needs V_j in shared memory.
-            const int j = pv_next[qt];
-            if (j < s_next[qt]) {
-              const uint32_t v_addr = smem_u32(smem + Smem2::v + (j % NV) * TILE_BYTES);
-              const uint32_t p_tmem = tmem_base + qt * 128;          // packed bf16: 8 columns per K=16 step
-              const uint32_t d = tmem_base + 256 + qt * 128;
-              if (pv_half[qt] == 0 && mbar_test_wait(&bars[P_FULL + qt], j & 1) && mbar_test_wait(&bars[V_FULL + j % NV], (j / NV) & 1)) {
-                tc_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < BKV / 32; ++kk)
-                  umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, (j | kk) != 0);
-                pv_half[qt] = 1;
-                CE_EVT(j, 3)
-                progress = true;
-              }
-              if (pv_half[qt] == 1 && mbar_test_wait(&bars[P_FULL + 2 + qt], j & 1)) {
-                tc_fence_after();
-#pragma unroll
-                for (int kk = BKV / 32; kk < BKV / 16; ++kk)
-                  umma_bf16_ts(d, p_tmem + kk * 8, umma_desc_mnmajor_sw128(v_addr + kk * 2048, HALF_BYTES), IDESC_PV, 1);
-                umma_commit(&bars[PV_DONE + qt]);
-                CE_EVT(j, 4)
-                pv_half[qt] = 0;
-                ++pv_next[qt];
-                if (pv_next[qt ^ 1] > j) umma_commit(&bars[V_EMPTY + j % NV]);  // both query tiles have consumed V_j
-                progress = true;
-                try_s();  // S_qt(j+1) right behind P.V_qt(j)
-              }
+            for (int part = 0; part < PARTS; ++part) {
+              if (SPIN) mbar_spin(&bars[P_FULL + part * 2 + qt], j & 1, 40 + qt);
+              else mbar_wait(&bars[P_FULL + part * 2 + qt], j & 1, 40 + qt);
+              if (part == 0 && qt == 0) mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 44);
+              tc_fence_after();
+              if (QUARTERS) umma_bf16_ts_x2(d, p_tmem + part * 16, 8, dv[2 * part], dv[2 * part + 1], IDESC_PV, (j | part) != 0);
+              else umma_bf16_ts_x4(d, p_tmem + part * 32, 8, dv[4 * part], dv[4 * part + 1], dv[4 * part + 2], dv[4 * part + 3], IDESC_PV, (j | part) != 0);
+              if (part == 0) { CE_EVT(j, 3) }
             }
-          }
-          if (progress) {
-            idle = 0;
-          } else if ((++idle & 0xFFF) == 0) {
-            if (t_start == 0) t_start = global_timer_ns();
-            else if (global_timer_ns() - t_start > CE_MBAR_TIMEOUT_NS) {
-              printf("[chronoedit_b200] attention2 MMA stalled: block=(%d,%d,%d) s=%d,%d pv=%d,%d\n", blockIdx.x, blockIdx.y, blockIdx.z, s_next[0],
-                     s_next[1], pv_next[0], pv_next[1]);
-              __trap();
-            }
+            umma_commit(&bars[PV_DONE + qt]);
+            if (qt == 1) umma_commit(&bars[V_EMPTY + j % NV]);   // both query tiles have consumed V_j
+            CE_EVT(j, 4)
+            if (j + 1 < n_tiles) issue_s(qt, j + 1);
           }
         }
+#undef CE_EVT
       }
     }
   } else {
@@ -310,7 +203,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t o_tmem = tmem_base + lane_base + 256 + qt * 128;
     const float sl2 = a.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    const bool timed = a.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 128 || threadIdx.x == 256);
+    const bool timed = timed_blk && (threadIdx.x == 128 || threadIdx.x == 256);
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tc0 = 0;
 #define CE_TICK(slot)                      \
@@ -319,14 +212,17 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     tacc[slot] += _t - tc0;                \
     tc0 = _t;                              \
   }
+#define CE_SEVT(slot) \
+  if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + (slot)] = clock64();
     if (timed) tc0 = clock64();
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = a.Lk - j * BKV;
-      mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
+      if (SPIN) mbar_spin(&bars[S_FULL + qt], j & 1, 60 + qt);
+      else mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
       CE_TICK(0)
-      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 0] = clock64();
+      CE_SEVT(0)
       uint32_t s[128];
       uint32_t pk[64];
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
@@ -426,23 +322,63 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
         }
         negm_2 = f2_pack(-m, -m);
+        if (!QUARTERS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) exp_pair(i);
+          for (int i = 0; i < 32; ++i) exp_pair(i);
+        }
       }
-      // P (packed bf16, 64 columns) overwrites the first half of this group's S region, published in two halves so that
-      // the tensor pipe starts on P.V while the second half is still being exponentiated
+      // P (packed bf16, 64 columns) overwrites the first half of this group's S region and is published part by part, so that
+      // the tensor pipe works on P.V while the rest of the row is still being exponentiated
       tc_fence_after();
-      tmem_st_32x32(s_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      if (QUARTERS) {
+        if (!first_half_done) {
 #pragma unroll
-      for (int i = 32; i < 40; ++i) exp_pair(i);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bars[P_FULL + qt]);
-      CE_TICK(3)
-      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 1] = clock64();
+          for (int i = 0; i < 16; ++i) exp_pair(i);
+        }
+        tmem_st_32x16(s_tmem, &pk[0]);
+        if (!first_half_done) {
 #pragma unroll
-      for (int i = 40; i < 64; ++i) exp_pair(i);
-      tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+          for (int i = 16; i < 20; ++i) exp_pair(i);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[P_FULL + 0 + qt]);
+        if (!first_half_done) {
+#pragma unroll
+          for (int i = 20; i < 32; ++i) exp_pair(i);
+        }
+        tmem_st_32x16(s_tmem + 16, &pk[16]);
+#pragma unroll
+        for (int i = 32; i < 36; ++i) exp_pair(i);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[P_FULL + 2 + qt]);
+        CE_TICK(3)
+        CE_SEVT(1)
+#pragma unroll
+        for (int i = 36; i < 48; ++i) exp_pair(i);
+        tmem_st_32x16(s_tmem + 32, &pk[32]);
+#pragma unroll
+        for (int i = 48; i < 52; ++i) exp_pair(i);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[P_FULL + 4 + qt]);
+#pragma unroll
+        for (int i = 52; i < 64; ++i) exp_pair(i);
+        tmem_st_32x16(s_tmem + 48, &pk[48]);
+      } else {
+        tmem_st_32x32(s_tmem, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+#pragma unroll
+        for (int i = 32; i < 40; ++i) exp_pair(i);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[P_FULL + 0 + qt]);
+        CE_TICK(3)
+        CE_SEVT(1)
+#pragma unroll
+        for (int i = 40; i < 64; ++i) exp_pair(i);
+        tmem_st_32x32(s_tmem + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+      }
       {
         float a0, a1, b0, b1;
         f2_unpack(f2_add(sum2[0], sum2[1]), a0, a1);
@@ -451,14 +387,16 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bars[P_FULL + 2 + qt]);
+      mbar_arrive(&bars[P_FULL + (PARTS - 1) * 2 + qt]);
       CE_TICK(4)
-      if (timed && j >= 16 && j < 24) a.timing[64 + qt * 64 + (j - 16) * 8 + 2] = clock64();
+      CE_SEVT(2)
     }
     if (timed && qt == 0) {
       for (int i = 0; i < 5; ++i) a.timing[i] = tacc[i];
       a.timing[5] = n_tiles;
     }
+#undef CE_TICK
+#undef CE_SEVT
 
     // ---- normalise and store this query tile
     mbar_wait(&bars[PV_DONE + qt], (n_tiles - 1) & 1, 80 + qt);
@@ -507,37 +445,44 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap2(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap2(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap2(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
-  // developer knobs: CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..2); CE_ATTN_SPEC=1 turns the
-  // speculative (previous-maximum) order of the softmax on; CE_ATTN_FIXED=0 goes back to the event-driven issuer / producer
+  // developer knobs (A/B): CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..3); CE_ATTN_SPEC=1 speculative
+  // (previous-maximum) softmax order; CE_ATTN_SPIN=1 spinning waits on the critical chain; CE_ATTN_QUARTERS=1 P in four parts
   static const int poly = [] {
     const char* e = getenv("CE_ATTN_POLY");
-    const int v = e ? atoi(e) : 0;
-    return v < 0 ? 0 : (v > 2 ? 2 : v);
+    const int v = e ? atoi(e) : CE_ATTN_POLY_DEFAULT;
+    return v < 0 ? 0 : (v > 3 ? 3 : v);
   }();
-  static const bool spec = [] {
-    const char* e = getenv("CE_ATTN_SPEC");
-    return e && e[0] == '1';
-  }();
-  static const bool fixed = [] {
-    const char* e = getenv("CE_ATTN_FIXED");
-    return !(e && e[0] == '0');
-  }();
+  auto flag = [](const char* name, bool dflt) {
+    const char* e = getenv(name);
+    return e ? e[0] == '1' : dflt;
+  };
+  static const bool spec = flag("CE_ATTN_SPEC", CE_ATTN_SPEC_DEFAULT);
+  static const bool spin = flag("CE_ATTN_SPIN", CE_ATTN_SPIN_DEFAULT);
+  static const bool quarters = flag("CE_ATTN_QUARTERS", CE_ATTN_QUARTERS_DEFAULT);
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-#define CE_LAUNCH_ATTN2(P, S, F)                                                                         \
-  do {                                                                                                   \
-    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S, F>), Smem2::total);                                      \
-    attention2_fwd_kernel<P, S, F><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);        \
+#define CE_LAUNCH_ATTN2(P, S, N, Q)                                                                         \
+  do {                                                                                                      \
+    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S, N, Q>), Smem2::total);                                      \
+    attention2_fwd_kernel<P, S, N, Q><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);        \
   } while (0)
-#define CE_LAUNCH_ATTN2_P(S, F)                       \
-  switch (poly) {                                     \
-    case 0: CE_LAUNCH_ATTN2(0, S, F); break;          \
-    case 1: CE_LAUNCH_ATTN2(1, S, F); break;          \
-    default: CE_LAUNCH_ATTN2(2, S, F); break;         \
+#define CE_LAUNCH_ATTN2_P(S, N, Q)                       \
+  switch (poly) {                                        \
+    case 0: CE_LAUNCH_ATTN2(0, S, N, Q); break;          \
+    case 1: CE_LAUNCH_ATTN2(1, S, N, Q); break;          \
+    case 2: CE_LAUNCH_ATTN2(2, S, N, Q); break;          \
+    default: CE_LAUNCH_ATTN2(3, S, N, Q); break;         \
   }
-  if (spec && fixed) { CE_LAUNCH_ATTN2_P(true, true) }
-  else if (spec) { CE_LAUNCH_ATTN2_P(true, false) }
-  else if (fixed) { CE_LAUNCH_ATTN2_P(false, true) }
-  else { CE_LAUNCH_ATTN2_P(false, false) }
+  const int variant = (spec ? 4 : 0) | (spin ? 2 : 0) | (quarters ? 1 : 0);
+  switch (variant) {
+    case 0: CE_LAUNCH_ATTN2_P(false, false, false) break;
+    case 1: CE_LAUNCH_ATTN2_P(false, false, true) break;
+    case 2: CE_LAUNCH_ATTN2_P(false, true, false) break;
+    case 3: CE_LAUNCH_ATTN2_P(false, true, true) break;
+    case 4: CE_LAUNCH_ATTN2_P(true, false, false) break;
+    case 5: CE_LAUNCH_ATTN2_P(true, false, true) break;
+    case 6: CE_LAUNCH_ATTN2_P(true, true, false) break;
+    default: CE_LAUNCH_ATTN2_P(true, true, true) break;
+  }
 #undef CE_LAUNCH_ATTN2_P
 #undef CE_LAUNCH_ATTN2
   CE_CHECK_CUDA(cudaGetLastError());

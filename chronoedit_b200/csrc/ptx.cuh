@@ -89,6 +89,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Spinning wait (test_wait never suspends the thread): lowest wake-up latency, for the one or two threads whose reaction time is
+// on a critical chain.  Same wall-clock bound as mbar_wait.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_test_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xFFFF) == 0) {
+      if (t0 == 0) t0 = global_timer_ns();
+      else if (global_timer_ns() - t0 > CE_MBAR_TIMEOUT_NS) {
+        printf("[chronoedit_b200] mbarrier (spin) timeout: tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -242,6 +260,18 @@ __device__ __forceinline__ void umma_bf16_ts_x4(uint32_t tmem_d, uint32_t tmem_a
       "r"(tmem_a), "r"(a1), "r"(a2), "r"(a3), "l"(db0), "l"(db1), "l"(db2), "l"(db3), "r"(idesc), "r"(acc_first)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_ts_x2(uint32_t tmem_d, uint32_t tmem_a, uint32_t a_step, uint64_t db0, uint64_t db1, uint32_t idesc,
+                                                uint32_t acc_first) {
+  const uint32_t a1 = tmem_a + a_step;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %4, %5, q;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(a1), "l"(db0), "l"(db1), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
 // Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -277,6 +307,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
