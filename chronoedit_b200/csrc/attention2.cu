@@ -34,9 +34,8 @@ constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
 // defaults of the A/B knobs (chosen from profiles/r2*_attention_*.log)
-#define CE_ATTN_POLY_DEFAULT 0
+#define CE_ATTN_POLY_DEFAULT 1
 #define CE_ATTN_SPEC_DEFAULT false
-#define CE_ATTN_SPIN_DEFAULT false
 #define CE_ATTN_QUARTERS_DEFAULT false
 
 struct Smem2 {
@@ -63,9 +62,8 @@ enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_E
 //            coming from TMEM, the tile's own maximum is folded in between the MUFU instructions, and the tile is redone the
 //            classic way (max first) only when that maximum exceeds the running one by more than the lazy-rescale threshold --
 //            bit-identical results, because without a rescale the classic path uses the same stale maximum;
-//   SPIN     the waits on the critical chain (issuer: P published; softmax: S ready) spin on test_wait instead of suspending;
 //   QUARTERS P is published (and P.V issued) in four 32-key parts instead of two 64-key halves.
-template <int POLY8, bool SPEC, bool SPIN, bool QUARTERS>
+template <int POLY8, bool SPEC, bool QUARTERS>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
@@ -175,8 +173,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             const uint32_t d = tmem_base + 256 + qt * 128;
 #pragma unroll
             for (int part = 0; part < PARTS; ++part) {
-              if (SPIN) mbar_spin(&bars[P_FULL + part * 2 + qt], j & 1, 40 + qt);
-              else mbar_wait(&bars[P_FULL + part * 2 + qt], j & 1, 40 + qt);
+              mbar_wait(&bars[P_FULL + part * 2 + qt], j & 1, 40 + qt);   // (spinning here instead of try_wait: measured -3.5 %)
               if (part == 0 && qt == 0) mbar_wait(&bars[V_FULL + j % NV], (j / NV) & 1, 44);
               tc_fence_after();
               if (QUARTERS) umma_bf16_ts_x2(d, p_tmem + part * 16, 8, dv[2 * part], dv[2 * part + 1], IDESC_PV, (j | part) != 0);
@@ -218,8 +215,7 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = a.Lk - j * BKV;
-      if (SPIN) mbar_spin(&bars[S_FULL + qt], j & 1, 60 + qt);
-      else mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
+      mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
       CE_TICK(0)
       CE_SEVT(0)
@@ -445,43 +441,37 @@ int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap2(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap2(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap2(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
-  // developer knobs (A/B): CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA pipe (0..3); CE_ATTN_SPEC=1 speculative
-  // (previous-maximum) softmax order; CE_ATTN_SPIN=1 spinning waits on the critical chain; CE_ATTN_QUARTERS=1 P in four parts
+  // developer knobs (A/B, profiles/r2g_attention_variant_sweep.log): CE_ATTN_POLY = how many of every 8 exp2 pairs run on the FMA
+  // pipe (0..2; 1 is +2.3 %, 2 is +0.7 %, 3 is 0); CE_ATTN_SPEC=1 speculative (previous-maximum) softmax order (0 +- 1 %);
+  // CE_ATTN_QUARTERS=1 P in four parts (+0.7 %, nothing on top of POLY=1)
   static const int poly = [] {
     const char* e = getenv("CE_ATTN_POLY");
     const int v = e ? atoi(e) : CE_ATTN_POLY_DEFAULT;
-    return v < 0 ? 0 : (v > 3 ? 3 : v);
+    return v < 0 ? 0 : (v > 2 ? 2 : v);
   }();
   auto flag = [](const char* name, bool dflt) {
     const char* e = getenv(name);
     return e ? e[0] == '1' : dflt;
   };
   static const bool spec = flag("CE_ATTN_SPEC", CE_ATTN_SPEC_DEFAULT);
-  static const bool spin = flag("CE_ATTN_SPIN", CE_ATTN_SPIN_DEFAULT);
   static const bool quarters = flag("CE_ATTN_QUARTERS", CE_ATTN_QUARTERS_DEFAULT);
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-#define CE_LAUNCH_ATTN2(P, S, N, Q)                                                                         \
-  do {                                                                                                      \
-    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S, N, Q>), Smem2::total);                                      \
-    attention2_fwd_kernel<P, S, N, Q><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);        \
+#define CE_LAUNCH_ATTN2(P, S, Q)                                                                      \
+  do {                                                                                                \
+    CE_ENSURE_SMEM((attention2_fwd_kernel<P, S, Q>), Smem2::total);                                   \
+    attention2_fwd_kernel<P, S, Q><<<grid, ATTN2_THREADS, Smem2::total, stream>>>(tq, tk, tv, a);     \
   } while (0)
-#define CE_LAUNCH_ATTN2_P(S, N, Q)                       \
-  switch (poly) {                                        \
-    case 0: CE_LAUNCH_ATTN2(0, S, N, Q); break;          \
-    case 1: CE_LAUNCH_ATTN2(1, S, N, Q); break;          \
-    case 2: CE_LAUNCH_ATTN2(2, S, N, Q); break;          \
-    default: CE_LAUNCH_ATTN2(3, S, N, Q); break;         \
+#define CE_LAUNCH_ATTN2_P(S, Q)                       \
+  switch (poly) {                                     \
+    case 0: CE_LAUNCH_ATTN2(0, S, Q); break;          \
+    case 1: CE_LAUNCH_ATTN2(1, S, Q); break;          \
+    default: CE_LAUNCH_ATTN2(2, S, Q); break;         \
   }
-  const int variant = (spec ? 4 : 0) | (spin ? 2 : 0) | (quarters ? 1 : 0);
-  switch (variant) {
-    case 0: CE_LAUNCH_ATTN2_P(false, false, false) break;
-    case 1: CE_LAUNCH_ATTN2_P(false, false, true) break;
-    case 2: CE_LAUNCH_ATTN2_P(false, true, false) break;
-    case 3: CE_LAUNCH_ATTN2_P(false, true, true) break;
-    case 4: CE_LAUNCH_ATTN2_P(true, false, false) break;
-    case 5: CE_LAUNCH_ATTN2_P(true, false, true) break;
-    case 6: CE_LAUNCH_ATTN2_P(true, true, false) break;
-    default: CE_LAUNCH_ATTN2_P(true, true, true) break;
+  switch ((spec ? 2 : 0) | (quarters ? 1 : 0)) {
+    case 0: CE_LAUNCH_ATTN2_P(false, false) break;
+    case 1: CE_LAUNCH_ATTN2_P(false, true) break;
+    case 2: CE_LAUNCH_ATTN2_P(true, false) break;
+    default: CE_LAUNCH_ATTN2_P(true, true) break;
   }
 #undef CE_LAUNCH_ATTN2_P
 #undef CE_LAUNCH_ATTN2
