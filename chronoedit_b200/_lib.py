@@ -32,6 +32,12 @@ class DiTConfigC(ctypes.Structure):
     ]
 
 
+class EncoderConfigC(ctypes.Structure):   # ce_encoder_config
+    _fields_ = [("kind", c_int32), ("vocab_size", c_int32), ("d_model", c_int32), ("d_kv", c_int32), ("d_ff", c_int32),
+                ("num_layers", c_int32), ("num_heads", c_int32), ("eps", c_float), ("image_size", c_int32), ("patch_size", c_int32),
+                ("hidden_act", c_int32)]
+
+
 class UniPCStepArgsC(ctypes.Structure):   # ce_unipc_step_args (field order = include/chronoedit_b200.h)
     _fields_ = [
         ("sample_dtype", c_int32), ("model_dtype", c_int32), ("n", c_int64), ("cond", c_void_p), ("uncond", c_void_p),
@@ -74,6 +80,13 @@ SIGNATURES = {
     "ce_dit_last_launch_count": (c_int64, [c_void_p]),
     "ce_dit_profile_begin": (c_int, [c_void_p, c_int]),
     "ce_dit_profile_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ce_encoder_create": (c_int, [POINTER(EncoderConfigC), POINTER(c_void_p)]),
+    "ce_encoder_destroy": (None, [c_void_p]),
+    "ce_encoder_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "ce_encoder_workspace_bytes": (c_int64, [c_void_p, c_int, c_int]),
+    "ce_encoder_last_launch_count": (c_int64, [c_void_p]),
+    "ce_umt5_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "ce_clip_vision_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "ce_vae_create": (c_int, [c_void_p, POINTER(c_void_p)]),
     "ce_vae_destroy": (None, [c_void_p]),
     "ce_vae_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),

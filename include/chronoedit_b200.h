@@ -177,6 +177,44 @@ int ce_vae_decode(ce_vae* h, const void* z, void* video, int latent_frames, int 
 int64_t ce_vae_last_launch_count(const ce_vae* h);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Encoders in front of the loop, once per edit:
+ *   transformers.UMT5EncoderModel   -- pipeline_chronoedit.py:205-244  self.text_encoder(ids, mask).last_hidden_state
+ *   transformers.CLIPVisionModel    -- pipeline_chronoedit.py:246-254  self.image_encoder(**image, output_hidden_states=True).hidden_states[-2]
+ * Parameters are registered by their transformers state_dict names, bf16, with these host-side fusions:
+ *   UMT5: "encoder.block.N.layer.0.SelfAttention.qk.weight" [2*H*d_kv, d_model] = rows of q | k;   "shared.weight" [vocab, d_model]
+ *   CLIP: "vision_model.encoder.layers.N.self_attn.qk_proj.{weight,bias}" = q | k;  patch_embedding.weight flattened [D, 3*ps*ps] with K padded
+ *         to a multiple of 8;  every LayerNorm additionally as fp32 "<name>.weight_f32" / "<name>.bias_f32" [D].
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ce_encoder ce_encoder;
+typedef struct ce_encoder_config {
+  int32_t kind;          /* 0 = UMT5 text encoder, 1 = CLIP vision encoder */
+  int32_t vocab_size;    /* UMT5: 256384 */
+  int32_t d_model;       /* 4096 | 1280 */
+  int32_t d_kv;          /* head dim: 64 | 80 */
+  int32_t d_ff;          /* 10240 | 5120 */
+  int32_t num_layers;    /* 24 | 32 */
+  int32_t num_heads;     /* 64 | 16 */
+  float eps;             /* 1e-6 | 1e-5 */
+  int32_t image_size;    /* CLIP: 224 */
+  int32_t patch_size;    /* CLIP: 14 */
+  int32_t hidden_act;    /* CLIP: 0 = quick_gelu, 1 = gelu (erf) */
+} ce_encoder_config;
+int ce_encoder_create(const ce_encoder_config* cfg, ce_encoder** out);
+void ce_encoder_destroy(ce_encoder* h);
+int ce_encoder_set_weight(ce_encoder* h, const char* name, const void* ptr, int64_t numel);
+int64_t ce_encoder_workspace_bytes(const ce_encoder* h, int batch, int seq_len);   /* CLIP: seq_len = 1 + (image_size/patch_size)^2 */
+int64_t ce_encoder_last_launch_count(const ce_encoder* h);
+/* input_ids [B, L] int64 (device); valid_len_host[b] = number of leading unmasked tokens (HOST array; the tokenizer pads on the right);
+ * bias_tables [num_layers, H, 2L-1] bf16 (device): relative_attention_bias of layer l, head h at relative position (key - query) + L - 1
+ * (the bucket function is host code, chronoedit_b200/encoders.py);  last_hidden_state [B, L, d_model] bf16.  L must be a multiple of 8. */
+int ce_umt5_encode(ce_encoder* h, const int64_t* input_ids, const int32_t* valid_len_host, void* last_hidden_state, int batch,
+                   int seq_len, const void* bias_tables, void* workspace, int64_t workspace_bytes, void* stream);
+/* pixel_values [B, 3, S, S] bf16 -> hidden state after `layers_to_run` encoder layers [B, 1 + (S/ps)^2, d_model] bf16
+ * (hidden_states[-2] = num_layers - 1 layers; 0 = the embeddings after pre_layrnorm). */
+int ce_clip_vision_encode(ce_encoder* h, const void* pixel_values, void* out, int batch, int layers_to_run, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Individual hot-path operators (used by the handles above; exported for operator-level parity tests / profiling)
  * ------------------------------------------------------------------------------------------------------------ */
 
