@@ -434,7 +434,13 @@ def run_ours(args):
         _orig(i)
         launch_count["n"] += model.launches_per_forward() + 1   # + the fused sampler launch
 
+    if args.cuda_graph:   # replay the forward as one CUDA graph in the `value` pass (captured during warm-up: step 2 of a configuration)
+        model.use_cuda_graph = True
+        for i in range(2):
+            device_step(args.warmup + i)
+        model.clear_context_cache()
     dev_ms, wall_ms, _, clocks = timed(counted_step, args.steps, 0, sampler, profile=False)
+    model.use_cuda_graph = False
     launches = launch_count["n"]
     value = world * args.steps / (dev_ms / 1000.0)
     # pass 2 -- the per-class split (CUDA events around every launch; slightly slower, not the reported value)
@@ -536,6 +542,7 @@ def run_ours(args):
                                        "timed region, so the timed steps are the first steps of an edit and include computing it once; algorithmic "
                                        "FLOPs below stay un-hoisted (222.43 TFLOP/forward)"),
                 "ms_per_step_without_context_cache": nocache_ms,
+                "cuda_graph": bool(args.cuda_graph),
                 "timing": "value: CUDA events around the K steps, no per-launch events; roofline split: separate pass with an event pair per launch",
             },
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -586,6 +593,7 @@ def main():
     ap.add_argument("--layers", type=int, default=40, help="DEV ONLY: fewer layers make the number invalid as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the DiT forward as a CUDA graph in the value pass (A/B)")
     ap.add_argument("--no-context-cache", action="store_true", help="recompute the step-invariant context every step (round-1 behaviour)")
     ap.add_argument("--no-vae", action="store_true", help="skip the (untimed-region) VAE encode/decode measurement")
     ap.add_argument("--latent-frames", type=int, default=2, choices=[2, 8],

@@ -148,6 +148,7 @@ class ChronoEditTransformer3DModel(nn.Module):
         torch_dtype: torch.dtype = torch.bfloat16,
         device: Optional[Union[str, torch.device]] = None,
         cache_context: bool = False,
+        use_cuda_graph: bool = False,
     ) -> None:
         super().__init__()
         if torch_dtype != torch.bfloat16:
@@ -181,6 +182,10 @@ class ChronoEditTransformer3DModel(nn.Module):
         # opt-in hoisting of the step-invariant context (text / image embedders, cross-attention K/V of all blocks): see
         # `ce_dit_forward_ex` in include/chronoedit_b200.h.  Up to `_ctx_slots` (prompt, negative prompt) entries, LRU.
         self.cache_context = bool(cache_context)
+        # opt-in CUDA-graph replay of the forward: the ~590 launches of a forward are captured once per
+        # (geometry, context slot) and replayed; inputs are staged into fixed device buffers, the result is returned from one.
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs: Dict[Tuple, Dict[str, Any]] = {}
         self._ctx_slots = 2
         self._ctx_cache: list = []   # entries: dict(txt=, img=, txt_v=, img_v=, shape=, buf=)
         self._lora_adapters: Dict[str, Dict[str, torch.Tensor]] = {}
@@ -198,6 +203,7 @@ class ChronoEditTransformer3DModel(nn.Module):
     def _apply(self, fn, *a, **k):
         # .to()/.cuda()/.cpu() re-allocate parameters: the fused device buffers must be rebuilt
         self._packed = False
+        self._graphs = {}
         self._ctx_cache = []
         self._workspaces = {}
         return super()._apply(fn, *a, **k)
@@ -331,6 +337,7 @@ class ChronoEditTransformer3DModel(nn.Module):
         self._pack_keepalive = keep
         self._packed = True
         self._ctx_cache = []   # cached K/V were projected with the previous weights
+        self._graphs = {}
 
     def _workspace(self, B, T, H, W, Lt) -> torch.Tensor:
         key = (B, T, H, W, Lt, str(self.device))
@@ -391,7 +398,10 @@ class ChronoEditTransformer3DModel(nn.Module):
         caps: Dict[int, torch.Tensor] = {}
         if capture_layers:
             caps = {int(l): torch.empty(B * L_tok, Dm, dtype=torch.bfloat16, device=dev) for l in capture_layers}
-        self._native_forward(x, t, txt, img, out, b0, caps, encoder_hidden_states, encoder_hidden_states_image)
+        if self.use_cuda_graph and not caps and b0 is None:
+            out = self._graphed_forward(x, t, txt, img, encoder_hidden_states, encoder_hidden_states_image)
+        else:
+            self._native_forward(x, t, txt, img, out, b0, caps, encoder_hidden_states, encoder_hidden_states_image)
         self.last_block0 = b0
         self.last_captures = caps
         if not return_dict:
@@ -422,6 +432,54 @@ class ChronoEditTransformer3DModel(nn.Module):
         finally:
             if caps:
                 check(L.ce_dit_set_capture(self._handle, None, None, 0))
+
+    def _graphed_forward(self, x, t, txt, img, txt_in, img_in) -> torch.Tensor:
+        """Replay (or, the second time a configuration is seen, capture) the forward as one CUDA graph.  A configuration = geometry +
+        the context-cache slot in use (its buffer address is baked into the captured launches).  The first call of a configuration
+        runs eagerly: it packs weights, builds RoPE tables, opts kernels into their shared-memory sizes and fills the context cache
+        -- none of which may happen during capture.  Inputs are copied into fixed staging tensors; the returned sample is a fresh
+        tensor (a copy out of the graph's fixed output buffer)."""
+        if not self._packed:
+            self.pack_weights()
+        ctx_buf, ctx_reuse = (None, 0)
+        if self.cache_context:
+            ctx_buf, ctx_reuse = self._context_slot(txt_in, img_in, txt, img)
+        key = (tuple(x.shape), tuple(txt.shape), None if img is None else tuple(img.shape), None if ctx_buf is None else ctx_buf.data_ptr())
+        L = _lib.lib()
+        B, _, T, H, W = x.shape
+        Lt = txt.shape[1]
+
+        def launch(xs, ts, txts, imgs, outs, reuse):
+            ws = self._workspace(B, T, H, W, Lt)
+            with torch.cuda.device(self.device):
+                check(L.ce_dit_forward_ex(self._handle, ptr(xs), ptr(ts), ptr(txts), ptr(imgs), ptr(outs), B, T, H, W, Lt, ptr(ws), ws.numel(),
+                                          None, ptr(ctx_buf), ctx_buf.numel() if ctx_buf is not None else 0, reuse, current_stream()))
+
+        g = self._graphs.get(key)
+        if g is None or (self.cache_context and not ctx_reuse):
+            # eager: first sight of this configuration, or the context has to be (re)computed into the slot
+            out = torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16, device=self.device)
+            launch(x, t, txt, img, out, ctx_reuse)
+            if g is None:
+                self._graphs[key] = {"graph": None}
+            return out
+        if g["graph"] is None:   # second sight: capture (with ctx_reuse = 1 when the context cache is on)
+            st = {"x": x.clone(), "t": t.clone(), "txt": txt.clone(), "img": None if img is None else img.clone(),
+                  "out": torch.empty(B, self.config.out_channels, T, H, W, dtype=torch.bfloat16, device=self.device)}
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                launch(st["x"], st["t"], st["txt"], st["img"], st["out"], 1 if self.cache_context else 0)
+            g.update(st)
+            g["graph"] = graph
+        g["x"].copy_(x)
+        g["t"].copy_(t)
+        if not self.cache_context:   # with the context cache the captured launches do not read the encoder states at all
+            g["txt"].copy_(txt)
+            if img is not None:
+                g["img"].copy_(img)
+        g["graph"].replay()
+        return g["out"].clone()
 
     def _context_slot(self, txt_in, img_in, txt, img):
         """(cache buffer, reuse flag) for these encoder states.  A hit requires the SAME tensor objects the cache entry was

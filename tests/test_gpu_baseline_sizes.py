@@ -198,3 +198,37 @@ def test_dit_context_cache_is_bit_identical():
     b = cached(x, t, text, img, return_dict=False)[0]
     assert torch.equal(a, b)
     assert cached.launches_per_forward() == plain.launches_per_forward()
+
+
+@gpu
+@pytest.mark.parametrize("cache", [False, True])
+def test_dit_cuda_graph_replay_is_bit_identical(cache):
+    """use_cuda_graph=True: the forward is captured on the second call of a configuration and replayed afterwards; every call must
+    return exactly what the eager launch chain returns, with and without the context cache, across changing inputs."""
+    from oracle import cases
+
+    import chronoedit_b200 as ce
+
+    case = cases.DIT_CASES["tiny_b2"]
+    cfg = case.cfg
+
+    def build(**kw):
+        m = ce.ChronoEditTransformer3DModel(
+            patch_size=cfg.patch_size, num_attention_heads=cfg.num_attention_heads, attention_head_dim=cfg.attention_head_dim,
+            in_channels=cfg.in_channels, out_channels=cfg.out_channels, text_dim=cfg.text_dim, freq_dim=cfg.freq_dim,
+            ffn_dim=cfg.ffn_dim, num_layers=cfg.num_layers, eps=cfg.eps, image_dim=cfg.image_dim,
+            added_kv_proj_dim=cfg.added_kv_proj_dim, **kw)
+        m.load_state_dict(cases.to_bf16_state(cases.dit_weights(case)))
+        return m.cuda()
+
+    x, t, text, img = (a.cuda() for a in cases.dit_inputs(case))
+    text, img = text.bfloat16(), img.bfloat16()
+    neg = torch.randn_like(text)
+    eager, graphed = build(), build(use_cuda_graph=True, cache_context=cache)
+    for step in range(5):
+        xs, ts = x + 0.05 * step, t - 77 * step
+        for ctx in (text, neg):
+            a = eager(xs, ts, ctx, img, return_dict=False)[0]
+            b = graphed(xs, ts, ctx, img, return_dict=False)[0]
+            assert torch.equal(a, b), f"step {step}: graph replay differs from the eager forward"
+    assert any(g.get("graph") is not None for g in graphed._graphs.values()), "no graph was ever captured"
