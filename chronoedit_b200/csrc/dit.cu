@@ -8,6 +8,7 @@
 //   -> attention(text) -> attention(image, += ) -> out-proj GEMM with y+x epilogue -> LN+modulate -> FFN-1 GEMM with
 //   bias+GELU epilogue -> FFN-2 GEMM with gate*y+x epilogue.
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -73,6 +74,7 @@ struct Workspace {
   bf16 *text1, *ctx_text, *img0, *img1, *img2, *ctx_img, *kv_text, *kv_img;
   bf16 *temb_bf16, *tproj;
   float *sin_emb, *h1, *temb_f32, *mod, *modf;
+  float2 *stats_x, *stats_qkv, *stats_q2;   // epilogue row statistics (GemmArgs::stats_out): [M, D/256], [M, 3D/256], [M, D/256]
   int64_t bytes;
 };
 
@@ -105,6 +107,10 @@ Workspace carve(const ce_dit_config& c, void* base, int B, int L, int Lt, int Li
   w.temb_f32 = b.take<float>((int64_t)B * D);
   w.mod = b.take<float>((int64_t)c.num_layers * B * 6 * D);
   w.modf = b.take<float>((int64_t)B * 2 * D);
+  const int64_t td = (D + 255) / 256;
+  w.stats_x = b.take<float2>(M * td);
+  w.stats_qkv = b.take<float2>(M * 3 * td);
+  w.stats_q2 = b.take<float2>(M * td);
   w.bytes = (b.off + 255) & ~int64_t(255);
   return w;
 }
@@ -287,8 +293,14 @@ static inline void prof_end(ce_dit* h, cudaStream_t s) {
   } while (0)
 
 static int linear(ce_dit* h, const bf16* A, int lda, const std::string& wname, int M, int N, int K, bf16* out, int ldo, int epi,
-                  const bf16* resid, int ldr, const float* gate, int gate_stride, int rows_per_batch, cudaStream_t s) {
+                  const bf16* resid, int ldr, const float* gate, int gate_stride, int rows_per_batch, cudaStream_t s,
+                  float2* stats_out = nullptr, int stats_mode = 0) {
   GemmArgs g;
+  if (stats_out) {
+    g.stats_out = stats_out;
+    g.stats_mode = stats_mode;
+    g.stats_ld = (N + gemm_tile_n(N) - 1) / gemm_tile_n(N);
+  }
   g.M = M; g.N = N; g.K = K;
   g.out = out; g.ldo = ldo;
   g.bias = W_BF16(wname + ".bias");
@@ -489,13 +501,26 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
   auto kv_text_of = [&](int layer) { return ctx_cache ? reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(ctx_cache) + layer * ctx_layer_bytes) : ws.kv_text; };
   auto kv_img_of = [&](int layer) { return ctx_cache ? kv_text_of(layer) + kv_t_elems : ws.kv_img; };
   const bool ctx_compute = !(ctx_cache && ctx_reuse);
+  // Row statistics for the LayerNorms / RMSNorms come from the epilogue of the GEMM that wrote the row whenever the N tiles (256 wide)
+  // line up with the q | k | v boundaries; the row kernels are then streaming passes (elementwise.cuh).  CE_DIT_STATS=0: the
+  // round-1 kernels that reduce over the row themselves (A/B, and the path for widths that are not a multiple of 256).
+  static const bool stats_env = [] {
+    const char* e = getenv("CE_DIT_STATS");
+    return !(e && e[0] == '0');
+  }();
+  const bool st = stats_env && D % 256 == 0 && D / 256 <= 32;
+  const int tD = D / 256;
+  auto ln = [&](const bf16* x, bf16* y, const float* scale, const float* shift, int mod_stride, int rpb, const float* w, const float* b, int is1p) {
+    return st ? launch_layernorm_stats(x, D, y, D, M, D, c.eps, scale, shift, mod_stride, rpb, w, b, is1p, ws.stats_x, tD, tD, 256, s)
+              : launch_layernorm(x, D, y, D, M, D, c.eps, scale, shift, mod_stride, rpb, w, b, s, is1p);
+  };
   h->launches = 0;
   const float attn_scale = 1.0f / sqrtf((float)c.attention_head_dim);
   const std::string ce_ = "condition_embedder.";
 
   // ---- patch embedding (Conv3d k=s=(1,2,2) as im2row + GEMM, :429-430)
   RUN(launch_patchify(reinterpret_cast<const bf16*>(hidden_states), ws.patches, B, c.in_channels, frames, height, width, s));
-  RUN2(linear(h, ws.patches, Kp, "patch_embedding", M, D, Kp, ws.x, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+  RUN2(linear(h, ws.patches, Kp, "patch_embedding", M, D, Kp, ws.x, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s, st ? ws.stats_x : nullptr, 1));
 
   // ---- condition embedder (:147-165)
   RUN(launch_timestep_sinusoid(timestep, ws.sin_emb, B, c.freq_dim, s));
@@ -528,10 +553,15 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
     const std::string p = "blocks." + std::to_string(i) + ".";
     const float* mod = ws.mod + (size_t)i * B * 6 * D;  // [B, 6, D]: shift, scale, gate, c_shift, c_scale, c_gate
     // 1. self-attention
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, s, 1));
-    RUN2(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv + D, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_k.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
+    RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, 1));
+    RUN2(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s, st ? ws.stats_qkv : nullptr, 2));
+    if (st) {
+      RUNC(CAT_ROWS, 8.0 * M * D, launch_rmsnorm_rope_stats(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), W_BF16(p + "attn1.norm_k.weight"), 2,
+                                                             h->rope_cos, h->rope_sin, L, c.attention_head_dim, ws.stats_qkv, 3 * tD, tD, s));
+    } else {
+      RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
+      RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(ws.qkv + D, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_k.weight"), h->rope_cos, h->rope_sin, L, c.attention_head_dim, s));
+    }
     {
       AttnArgs a;
       a.B = B; a.H = H; a.Lq = L; a.Lk = L;
@@ -542,12 +572,17 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
       a.scale = attn_scale;
       RUN2(attention(h, a, s));
     }
-    RUN2(linear(h, ws.attn, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s));
+    RUN2(linear(h, ws.attn, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s, st ? ws.stats_x : nullptr, 1));
     // 2. cross-attention
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, nullptr, nullptr, 0, 0, W_F32(p + "norm2.weight"), W_F32(p + "norm2.bias"), s));
+    RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, nullptr, nullptr, 0, 0, W_F32(p + "norm2.weight"), W_F32(p + "norm2.bias"), 0));
     bf16* q2 = ws.qkv;  // [M, D]
-    RUN2(linear(h, ws.xn, D, p + "attn2.to_q", M, D, D, q2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+    RUN2(linear(h, ws.xn, D, p + "attn2.to_q", M, D, D, q2, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s, st ? ws.stats_q2 : nullptr, 2));
+    if (st) {
+      RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope_stats(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, 1, nullptr, nullptr, 0,
+                                                             c.attention_head_dim, ws.stats_q2, tD, tD, s));
+    } else {
+      RUNC(CAT_ROWS, 4.0 * M * D, launch_rmsnorm_rope(q2, D, M, D, c.eps, W_BF16(p + "attn2.norm_q.weight"), nullptr, nullptr, 0, c.attention_head_dim, s));
+    }
     bf16* kv_text = kv_text_of(i);
     bf16* kv_img = kv_img_of(i);
     if (ctx_compute) {
@@ -573,11 +608,11 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
       a.scale = attn_scale;
       RUN2(attention(h, a, s));
     }
-    RUN2(linear(h, ws.attn, D, p + "attn2.to_out.0", M, D, D, ws.x, D, EPI_BIAS_RESID, ws.x, D, nullptr, 0, 1, s));
+    RUN2(linear(h, ws.attn, D, p + "attn2.to_out.0", M, D, D, ws.x, D, EPI_BIAS_RESID, ws.x, D, nullptr, 0, 1, s, st ? ws.stats_x : nullptr, 1));
     // 3. feed-forward
-    RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, s, 1));
+    RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, mod + 4 * D, mod + 3 * D, 6 * D, L, nullptr, nullptr, 1));
     RUN2(linear(h, ws.xn, D, p + "ffn.net.0.proj", M, F, D, ws.hbuf, F, EPI_BIAS_GELU_TANH, nullptr, 0, nullptr, 0, 1, s));
-    RUN2(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s));
+    RUN2(linear(h, ws.hbuf, F, p + "ffn.net.2", M, D, F, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 5 * D, 6 * D, L, s, st ? ws.stats_x : nullptr, 1));
     if (i == 0 && block0_out)
       CE_CHECK_CUDA(cudaMemcpyAsync(block0_out, ws.x, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
     for (const auto& cap : h->capture)
@@ -585,7 +620,7 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
   }
 
   // ---- output head (:451-467): modf = [B, 2, D] with shift = chunk 0, scale = chunk 1
-  RUNC(CAT_ROWS, 4.0 * M * D, launch_layernorm(ws.x, D, ws.xn, D, M, D, c.eps, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, s, 1));
+  RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, 1));
   RUN2(linear(h, ws.xn, D, "proj_out", M, No, D, ws.yout, No, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
   RUN(launch_unpatchify(ws.yout, No, reinterpret_cast<bf16*>(sample), B, c.out_channels, frames, height, width, s));
   return CE_OK;

@@ -32,6 +32,139 @@ __device__ __forceinline__ float2 pair_sum(float a, float b, float2* part) {
   return make_float2(a + o.x, b + o.y);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row statistics that arrive as per-(row, N tile) partials from the epilogue of the GEMM that produced the row (GemmArgs::stats_out):
+// each warp merges them with shuffles -- Chan's pairwise update for (mean, M2), always (lower lane, higher lane) so that every lane
+// ends with bit-identical values -- and the row kernel becomes a pure streaming pass: no reduction over the data, no barrier, loads
+// and stores of different vectors independent of each other.
+struct RowStat {
+  float n, mean, m2;
+};
+__device__ __forceinline__ RowStat chan_merge(const RowStat& a, const RowStat& b) {
+  const float tot = a.n + b.n;
+  if (tot == 0.f) return a;
+  const float delta = b.mean - a.mean, w = b.n / tot;
+  RowStat r;
+  r.n = tot;
+  r.mean = fmaf(delta, w, a.mean);
+  r.m2 = a.m2 + b.m2 + delta * delta * a.n * w;
+  return r;
+}
+__device__ __forceinline__ RowStat warp_merge_stats(const float2* __restrict__ partial, int tiles, int tile_n, int D) {
+  const int lane = threadIdx.x & 31;
+  RowStat s{0.f, 0.f, 0.f};
+  if (lane < tiles) {
+    const float2 p = partial[lane];
+    const int n = D - lane * tile_n;
+    s.n = (float)(n < tile_n ? n : tile_n);
+    s.mean = p.x;
+    s.m2 = p.y;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    RowStat t;
+    t.n = __shfl_xor_sync(0xffffffffu, s.n, o);
+    t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o);
+    t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
+    s = (lane & o) ? chan_merge(t, s) : chan_merge(s, t);
+  }
+  return s;
+}
+
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+layernorm_stats_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int mod_stride, int rows_per_batch,
+                       const float* __restrict__ weight, const float* __restrict__ bias, int scale_is_1p,
+                       const float2* __restrict__ stats, int stats_ld, int tiles, int tile_n) {
+  const int lane64 = threadIdx.x & 63;
+  const int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  if (row >= rows) return;
+  const RowStat st = warp_merge_stats(stats + (size_t)row * stats_ld, tiles, tile_n, D);
+  const float mean = st.mean;
+  const float rstd = rsqrtf(st.m2 / (float)D + eps);
+  const float nmr = -mean * rstd;
+  const int nvec = D >> 3;
+  const int b = row / rows_per_batch;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
+  uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
+  const float* pa = scale ? scale + (size_t)b * mod_stride : weight;
+  const float* pb = scale ? shift + (size_t)b * mod_stride : bias;
+#pragma unroll
+  for (int i = 0; i < HV; ++i) {
+    const int idx = lane64 + i * 64;
+    if (idx < nvec) {
+      float f[8], o[8];
+      unpack8(xr[idx], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], rstd, nmr);
+      if (pa) {
+        const float4* qa = reinterpret_cast<const float4*>(pa + idx * 8);
+        const float4* qb = reinterpret_cast<const float4*>(pb + idx * 8);
+        const float4 a0 = qa[0], a1 = qa[1], b0 = qb[0], b1 = qb[1];
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        if (scale && !scale_is_1p) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], 1.0f + av[j], bv[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], av[j], bv[j]);
+        }
+      }
+      yr[idx] = pack8(o);
+    }
+  }
+}
+
+// RMSNorm across heads (+ RoPE) from epilogue partial sums of squares; `nmat` matrices side by side in one row (q | k of the fused
+// QKV output): blockIdx.y selects the matrix (column offset y * D, its own weight and its own tile range)
+template <int HV>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
+rmsnorm_rope_stats_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight0,
+                          const bf16* __restrict__ weight1, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L,
+                          int head_dim, const float2* __restrict__ stats, int stats_ld, int tiles) {
+  const int lane64 = threadIdx.x & 63;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
+  if (row >= rows) return;
+  const int mat = blockIdx.y;
+  float ss = lane < tiles ? stats[(size_t)row * stats_ld + mat * tiles + lane].x : 0.f;
+  ss = warp_sum(ss);   // butterfly of commutative adds: identical in every lane
+  const float rstd = rsqrtf(ss / (float)D + eps);
+  const int nvec = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx + (size_t)mat * D);
+  const uint4* wr = reinterpret_cast<const uint4*>(mat ? weight1 : weight0);
+  const int tok = rope_cos ? row % L : 0;
+  const int half = head_dim >> 1;
+#pragma unroll
+  for (int i = 0; i < HV; ++i) {
+    const int idx = lane64 + i * 64;
+    if (idx < nvec) {
+      float f[8], w[8], o[8];
+      unpack8(xr[idx], f);
+      unpack8(wr[idx], w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round(f[j] * rstd) * w[j]);
+      if (rope_cos) {
+        const int c = idx * 8;
+        const int pair0 = (c % head_dim) >> 1;
+        const float4 cs = *reinterpret_cast<const float4*>(rope_cos + (size_t)tok * half + pair0);
+        const float4 sn = *reinterpret_cast<const float4*>(rope_sin + (size_t)tok * half + pair0);
+        const float cv[4] = {cs.x, cs.y, cs.z, cs.w};
+        const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float re = o[2 * p], im = o[2 * p + 1];
+          o[2 * p] = re * cv[p] - im * sv[p];
+          o[2 * p + 1] = re * sv[p] + im * cv[p];
+        }
+      }
+      xr[idx] = pack8(o);
+    }
+  }
+}
+
 template <int HV>
 __global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int rows, int D, float eps,
@@ -321,6 +454,45 @@ int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16
   else if (nvec <= 640) CE_RMS(10);
   else CE_RMS(16);
 #undef CE_RMS
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_layernorm_stats(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale, const float* shift,
+                           int mod_stride, int rows_per_batch, const float* weight, const float* bias, int scale_is_1p, const float2* stats,
+                           int stats_ld, int tiles, int tile_n, cudaStream_t stream) {
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D && ldx % 8 == 0 && ldy % 8 == 0, "layernorm(stats): shapes");
+  CE_REQUIRE(stats != nullptr && tiles >= 1 && tiles <= 32 && stats_ld >= tiles && tile_n > 0 && (tiles - 1) * tile_n < D && tiles * tile_n >= D,
+             "layernorm(stats): the tile partials must cover exactly [0, D) in at most 32 tiles");
+  CE_REQUIRE((scale == nullptr) == (shift == nullptr) && (weight == nullptr) == (bias == nullptr), "layernorm(stats): parameter pairs");
+  if (rows_per_batch <= 0) rows_per_batch = rows;
+  const int grid = (rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64);
+  const int nvec = D / 8;
+#define CE_LNS(V) layernorm_stats_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, y, ldy, rows, D, eps, scale, shift, mod_stride, rows_per_batch, weight, bias, scale_is_1p, stats, stats_ld, tiles, tile_n)
+  if (nvec <= 128) CE_LNS(2);
+  else if (nvec <= 256) CE_LNS(4);
+  else if (nvec <= 640) CE_LNS(10);
+  else CE_LNS(16);
+#undef CE_LNS
+  CE_CHECK_CUDA(cudaGetLastError());
+  return CE_OK;
+}
+
+int launch_rmsnorm_rope_stats(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight0, const bf16* weight1, int nmat,
+                              const float* rope_cos, const float* rope_sin, int L, int head_dim, const float2* stats, int stats_ld, int tiles,
+                              cudaStream_t stream) {
+  CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D && ldx % 8 == 0 && weight0 != nullptr, "rmsnorm(stats): shapes");
+  CE_REQUIRE(nmat == 1 || (nmat == 2 && weight1 != nullptr), "rmsnorm(stats): one or two matrices");
+  CE_REQUIRE(stats != nullptr && tiles >= 1 && tiles <= 32 && stats_ld >= nmat * tiles, "rmsnorm(stats): tile partials");
+  if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm(stats): rope table / head_dim");
+  dim3 grid((rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64), nmat);
+  const int nvec = D / 8;
+#define CE_RMSS(V) rmsnorm_rope_stats_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight0, weight1, rope_cos, rope_sin, L, head_dim, stats, stats_ld, tiles)
+  if (nvec <= 128) CE_RMSS(2);
+  else if (nvec <= 256) CE_RMSS(4);
+  else if (nvec <= 640) CE_RMSS(10);
+  else CE_RMSS(16);
+#undef CE_RMSS
   CE_CHECK_CUDA(cudaGetLastError());
   return CE_OK;
 }

@@ -19,6 +19,17 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, 
 int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight, const float* rope_cos,
                         const float* rope_sin, int L, int head_dim, cudaStream_t stream);
 
+// The same two operators when the row statistics come from the epilogue of the GEMM that produced x (GemmArgs::stats_out,
+// per-(row, N tile) partials): streaming kernels without a reduction or a barrier.  `tiles` partials of width tile_n cover [0, D).
+// The RMSNorm variant handles `nmat` (1 or 2) matrices lying side by side in a row (q | k of the fused QKV output): matrix m starts
+// at column m * D, uses weight m and partials [m * tiles, (m + 1) * tiles).
+int launch_layernorm_stats(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale, const float* shift,
+                           int mod_stride, int rows_per_batch, const float* weight, const float* bias, int scale_is_1p, const float2* stats,
+                           int stats_ld, int tiles, int tile_n, cudaStream_t stream);
+int launch_rmsnorm_rope_stats(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight0, const bf16* weight1, int nmat,
+                              const float* rope_cos, const float* rope_sin, int L, int head_dim, const float2* stats, int stats_ld, int tiles,
+                              cudaStream_t stream);
+
 // patches[(b,f,i,j), c*4 + dh*2 + dw] = x[b, c, f, 2i+dh, 2j+dw]   (im2row for the k=s=(1,2,2) patch-embedding conv, :368,429-430)
 int launch_patchify(const bf16* x, bf16* patches, int B, int C, int T, int H, int W, cudaStream_t stream);
 // out[b, c, f, 2i+dh, 2j+dw] = y[(b,f,i,j), (dh*2+dw)*C + c]       (unpatchify permute of :463-467)

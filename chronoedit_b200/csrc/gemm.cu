@@ -155,6 +155,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool row_ok = row < g.M;
       const int batch = row_ok ? row / g.rows_per_batch : 0;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      float st_pivot = 0.f, st_s = 0.f, st_ss = 0.f;   // row statistics of this tile (GemmArgs::stats_out)
+      int st_n = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = nb * BN + c * 32;
@@ -212,6 +214,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 for (int j = 0; j < 8; ++j) y[j] = x[j] + y[j];
               }
             }
+            if (g.stats_mode) {   // statistics of the values as stored (bf16), pivot-shifted inside the tile
+              float z[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) z[j] = bf16_round(y[j]);
+              if (st_n == 0) st_pivot = g.stats_mode == 1 ? z[0] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float d = z[j] - st_pivot;
+                st_s += d;
+                st_ss = fmaf(d, d, st_ss);
+              }
+              st_n += 8;
+            }
             uint4 o;
             o.x = pack_bf16x2(y[0], y[1]);
             o.y = pack_bf16x2(y[2], y[3]);
@@ -220,6 +235,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             *reinterpret_cast<uint4*>(g.out + (size_t)row * g.ldo + n) = o;
           }
         }
+      }
+      if (g.stats_mode && row_ok && st_n > 0) {
+        float2 pr;
+        if (g.stats_mode == 1) {   // (mean, M2) of this tile's st_n columns
+          const float md = st_s / (float)st_n;
+          pr = make_float2(st_pivot + md, fmaxf(st_ss - st_s * md, 0.f));
+        } else {
+          pr = make_float2(st_ss, 0.f);
+        }
+        g.stats_out[(size_t)row * g.stats_ld + nb] = pr;
       }
       tc_fence_before();
       __syncwarp();
@@ -271,6 +296,8 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
     CE_REQUIRE(g.resid != nullptr && g.ldr % 8 == 0, "gemm: residual epilogue needs resid / ldr");
   if (g.epi == EPI_BIAS_GATE_RESID)
     CE_REQUIRE(g.gate != nullptr && g.gate_stride % 4 == 0 && g.rows_per_batch > 0, "gemm: gate epilogue needs gate");
+  if (g.stats_mode) CE_REQUIRE(g.stats_out != nullptr && g.out != nullptr && g.stats_ld >= (g.N + gemm_tile_n(g.N) - 1) / gemm_tile_n(g.N) &&
+                               (g.stats_mode == 1 || g.stats_mode == 2), "gemm: stats_out / stats_ld / stats_mode");
   GemmArgs a = g;
   // Tiles are rasterised in groups of group_m M-tiles x all N-tiles so that the A panel of a group stays in L2 while the W
   // panels stream past it.  Measured at the 14B shapes (CE_GEMM_GROUP_M sweep, repeated A/B): 16 beats 8 by 2 % at K = 5120,
@@ -283,7 +310,7 @@ int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmA
     }();
     if (env_gm > 0) a.group_m = env_gm;
   }
-  const int bn = a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64);
+  const int bn = gemm_tile_n(a.N);
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)lda, BM);
   if (rc) return rc;

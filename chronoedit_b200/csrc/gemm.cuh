@@ -29,8 +29,19 @@ struct GemmArgs {
   const float* gate = nullptr;  // [batches, gate_stride] fp32, row -> batch = row / rows_per_batch
   int gate_stride = 0;
   int rows_per_batch = 1;
+  // Row statistics of the STORED bf16 output, one float2 per (row, N tile) at stats_out[row * stats_ld + n_tile]:
+  //   stats_mode 1: (mean, M2 = sum (y - mean)^2) of the tile's columns      -> FP32LayerNorm of the next operator
+  //   stats_mode 2: (sum y^2, 0)                                             -> RMSNorm across heads
+  // so that the row kernel that follows is a pure streaming pass (no reduction, no barrier); tiles are merged there in a fixed
+  // order (deterministic).  N tile width = gemm_tile_n(N).
+  float2* stats_out = nullptr;
+  int stats_ld = 0;
+  int stats_mode = 0;
   int group_m = 0;              // tile rasterisation: M-tiles per group (L2 reuse); 0 = chosen by launch_gemm_bf16
 };
+
+// N tile width launch_gemm_bf16 uses for a given N (the granularity of GemmArgs::stats_out)
+inline int gemm_tile_n(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
 
 // out[M,N] = epilogue(A[M,K] (row-major, lda) x W[N,K]^T (row-major = nn.Linear weight, ldw)).
 int launch_gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, const GemmArgs& g, cudaStream_t stream);

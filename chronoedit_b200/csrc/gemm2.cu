@@ -162,6 +162,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       const bool row_ok = row < g.M;
       const int batch = row_ok ? row / g.rows_per_batch : 0;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      float st_pivot = 0.f, st_s = 0.f, st_ss = 0.f;   // row statistics of this tile (GemmArgs::stats_out)
+      int st_n = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = nb * BN + c * 32;
@@ -217,10 +219,33 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                 for (int j = 0; j < 8; ++j) y[j] = x[j] + y[j];
               }
             }
+            if (g.stats_mode) {   // statistics of the values as stored (bf16), pivot-shifted inside the tile
+              float z[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) z[j] = bf16_round(y[j]);
+              if (st_n == 0) st_pivot = g.stats_mode == 1 ? z[0] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float d = z[j] - st_pivot;
+                st_s += d;
+                st_ss = fmaf(d, d, st_ss);
+              }
+              st_n += 8;
+            }
             *reinterpret_cast<uint4*>(g.out + (size_t)row * g.ldo + n) =
                 make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
           }
         }
+      }
+      if (g.stats_mode && row_ok && st_n > 0) {
+        float2 pr;
+        if (g.stats_mode == 1) {   // (mean, M2) of this tile's st_n columns
+          const float md = st_s / (float)st_n;
+          pr = make_float2(st_pivot + md, fmaxf(st_ss - st_s * md, 0.f));
+        } else {
+          pr = make_float2(st_ss, 0.f);
+        }
+        g.stats_out[(size_t)row * g.stats_ld + nb] = pr;
       }
       tc_fence_before();
       __syncwarp();
