@@ -66,6 +66,13 @@ SIGNATURES = {
     "ce_dit_context_cache_bytes": (c_int64, [c_void_p, c_int, c_int]),
     "ce_dit_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "ce_dit_sp_region_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "ce_dit_sp_configure": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64]),
+    "ce_ipc_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "ce_ipc_free": (c_int, [c_void_p]),
+    "ce_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
+    "ce_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ce_ipc_close": (c_int, [c_void_p]),
     "ce_dit_set_capture": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "ce_dit_host_staging_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "ce_dit_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -435,7 +435,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
   // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
   if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && attn_version() != 0)
-    return attn_version() == 5 ? launch_attention5(a, stream) : launch_attention2(a, stream);
+    return (attn_version() == 5 && a.peer_rows == 0) ? launch_attention5(a, stream) : launch_attention2(a, stream);
+  CE_REQUIRE(a.peer_rows == 0, "attention: the sequence-parallel output scatter is built into the self-attention kernel (attention2.cu) only");
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");
   CE_REQUIRE(a.q && a.k && a.v && a.out, "attention: null pointer");

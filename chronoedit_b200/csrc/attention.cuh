@@ -24,6 +24,12 @@ struct AttnArgs {
   int ldo = 0;
   float scale = 0.f;        // 1/sqrt(head_dim)
   long long* timing = nullptr;  // optional [16] device counters: phase cycles of softmax warp 4 lane 0 of block (0,0,0) (profiling aid)
+  // sequence-parallel output scatter (csrc/seqpar.cu): when peer_rows > 0, query row i of sample b is stored at
+  //   out_peer[i / peer_rows] + ((b * peer_rows + i % peer_rows) * ldo + h * head_dim + out_col0)
+  // i.e. straight into the attention-output buffer of the rank that owns that token (its own pointer or a peer's, NVLink).
+  bf16* out_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int peer_rows = 0;
+  int out_col0 = 0;
   int accumulate = 0;       // 1: out = bf16(float(bf16(attn)) + float(out))   (image + text cross-attention sum)
 };
 

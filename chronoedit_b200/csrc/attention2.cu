@@ -400,6 +400,8 @@ attention2_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const float inv = 1.0f / l;
     const int row = q0 + qt * BQ + r;
     bf16* orow = a.out + ((size_t)b * a.Lq + row) * a.ldo + h * HD;
+    if (a.peer_rows > 0 && row < a.Lq)   // sequence parallel: the token's owner gets the row (peer store over NVLink)
+      orow = a.out_peer[row / a.peer_rows] + ((size_t)b * a.peer_rows + row % a.peer_rows) * a.ldo + a.out_col0 + h * HD;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -434,6 +436,7 @@ int make_qkv_tmap2(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld
 
 int launch_attention2(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && a.Lk2 == 0 && a.accumulate == 0, "attention2: single source, no accumulate");
+  CE_REQUIRE(a.peer_rows == 0 || (a.Lq + a.peer_rows - 1) / a.peer_rows <= 8, "attention2: at most 8 sequence-parallel peers");
   CE_REQUIRE(a.head_dim == HD, "attention2: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention2: leading dims % 8");
   CUtensorMap tq, tk, tv;

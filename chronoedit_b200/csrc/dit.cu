@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "seqpar.cuh"
 
 namespace ce {
 const std::string& last_error();
@@ -42,6 +43,8 @@ struct ce_dit {
   int64_t launches = 0;
   // parity aid: output of selected blocks copied out (ce_dit_set_capture)
   std::vector<std::pair<int, void*>> capture;
+  // sequence parallelism (ce_dit_sp_configure): world == 1 means off
+  ce::SeqPar sp;
   // optional per-category device timing (CUDA events on the launch stream around every kernel)
   bool profiling = false;
   std::vector<cudaEvent_t> ev;       // pairs (begin, end)
@@ -415,6 +418,33 @@ int64_t ce_dit_context_cache_bytes(const ce_dit* h, int batch, int text_len) {
   return ((per_layer + 255) & ~int64_t(255)) * h->cfg.num_layers;
 }
 
+int64_t ce_dit_sp_region_bytes(const ce_dit* h, int batch, int frames, int height, int width, int world) {
+  if (!h || world < 2 || world > 8 || batch < 1) return -1;
+  const ce_dit_config& c = h->cfg;
+  const int64_t L = (int64_t)frames * (height / c.patch_h) * (width / c.patch_w);
+  if (L % world != 0 || c.num_attention_heads % world != 0) return -1;
+  return sp_layout(batch, L, D_of(c), (int64_t)c.out_channels * 4, world).bytes;
+}
+
+int ce_dit_sp_configure(ce_dit* h, int rank, int world, void* const* region_ptrs, int64_t region_bytes) {
+  CE_REQUIRE(h, "ce_dit_sp_configure: null handle");
+  if (world <= 1) {
+    h->sp = SeqPar();
+    return CE_OK;
+  }
+  CE_REQUIRE(world <= 8 && rank >= 0 && rank < world && region_ptrs && region_bytes > 0, "ce_dit_sp_configure: arguments");
+  CE_REQUIRE(h->cfg.num_attention_heads % world == 0, "ce_dit_sp_configure: the head count must be divisible by the number of ranks");
+  h->sp = SeqPar();
+  h->sp.rank = rank;
+  h->sp.world = world;
+  h->sp.region_bytes = region_bytes;
+  for (int w = 0; w < world; ++w) {
+    CE_REQUIRE(region_ptrs[w] != nullptr, "ce_dit_sp_configure: null region pointer");
+    h->sp.region[w] = reinterpret_cast<uint8_t*>(region_ptrs[w]);
+  }
+  return CE_OK;
+}
+
 int ce_dit_set_capture(ce_dit* h, const int32_t* layers, void* const* dst, int n) {
   CE_REQUIRE(h && n >= 0 && (n == 0 || (layers && dst)), "ce_dit_set_capture: arguments");
   h->capture.clear();
@@ -483,13 +513,24 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
              "ce_dit_forward: encoder_hidden_states_image must be given iff the model has an image embedder");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_v);
   const int B = batch, hp = height / c.patch_h, wp = width / c.patch_w;
-  const int L = frames * hp * wp, M = B * L, D = D_of(c), F = c.ffn_dim, H = c.num_attention_heads, Lt = text_len, Li = 257;
+  const int Lfull = frames * hp * wp, D = D_of(c), F = c.ffn_dim, H = c.num_attention_heads, Lt = text_len, Li = 257;
   const int Kp = c.in_channels * 4, No = c.out_channels * 4;
+  // sequence parallel: this rank owns tokens [tok0, tok0 + L) of every sample; everything below is written for "L local tokens"
+  SeqPar& sp = h->sp;
+  const bool spx = sp.world > 1;
+  if (spx) {
+    CE_REQUIRE(Lfull % sp.world == 0 && D % 256 == 0, "sequence parallel: tokens must divide by the rank count and the width by 256");
+    CE_REQUIRE(Lfull >= 256, "sequence parallel: at least 256 tokens (the self-attention kernel with the output scatter)");
+    CE_REQUIRE(!h->profiling && h->capture.empty() && block0_out == nullptr, "sequence parallel: no per-launch profiling / block capture");
+  }
+  const int L = spx ? Lfull / sp.world : Lfull, tok0 = spx ? sp.rank * L : 0, M = B * L;
+  const SpLayout lay = spx ? sp_layout(B, Lfull, D, No, sp.world) : SpLayout();
+  if (spx && lay.bytes > sp.region_bytes) return fail(CE_ERR_WORKSPACE, "sequence parallel: peer region too small (ce_dit_sp_region_bytes)");
   Workspace ws = carve(c, workspace, B, L, Lt, Li);
   if (ws.bytes > workspace_bytes)
     return fail(CE_ERR_WORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes, got " + std::to_string(workspace_bytes));
   CE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  if ((rc = ensure_rope(h, frames, hp, wp, s))) return rc;
+  if ((rc = ensure_rope(h, frames, hp, wp, s))) return rc;   // always the full table [Lfull, 64]
   // step-invariant context (text / image embedders and every block's cross-attention K/V, :52-60, :147-165): kept in the
   // caller's cache across the steps of one edit when one is given; recomputed into the workspace otherwise
   const int64_t kv_t_elems = (int64_t)B * Lt * 2 * D, kv_i_elems = c.image_dim > 0 ? (int64_t)B * Li * 2 * D : 0;
@@ -519,7 +560,8 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
   const std::string ce_ = "condition_embedder.";
 
   // ---- patch embedding (Conv3d k=s=(1,2,2) as im2row + GEMM, :429-430)
-  RUN(launch_patchify(reinterpret_cast<const bf16*>(hidden_states), ws.patches, B, c.in_channels, frames, height, width, s));
+  if (spx) RUN(launch_patchify_range(reinterpret_cast<const bf16*>(hidden_states), ws.patches, B, c.in_channels, frames, height, width, tok0, L, s));
+  else RUN(launch_patchify(reinterpret_cast<const bf16*>(hidden_states), ws.patches, B, c.in_channels, frames, height, width, s));
   RUN2(linear(h, ws.patches, Kp, "patch_embedding", M, D, Kp, ws.x, D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s, st ? ws.stats_x : nullptr, 1));
 
   // ---- condition embedder (:147-165)
@@ -555,6 +597,37 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
     // 1. self-attention
     RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, mod + 1 * D, mod + 0 * D, 6 * D, L, nullptr, nullptr, 1));
     RUN2(linear(h, ws.xn, D, p + "attn1.to_qkv", M, 3 * D, D, ws.qkv, 3 * D, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s, st ? ws.stats_qkv : nullptr, 2));
+    const bf16* attn_in = ws.attn;
+    if (spx) {
+      // heads <-> tokens exchange by peer stores: q | k normalised + rotated and scattered by head, v scattered by head, barrier,
+      // attention over ALL tokens for this rank's heads with the output rows scattered back to the ranks that own the tokens, barrier
+      const int Hl = H / sp.world, Dl = D / sp.world;
+      SpScatter sc;
+      sc.world = sp.world; sc.heads_per_rank = Hl; sc.L_total = Lfull; sc.rows_per_batch = L; sc.tok0 = tok0;
+      bf16* vdst[8];
+      for (int w = 0; w < sp.world; ++w) {
+        sc.dst[0][w] = reinterpret_cast<bf16*>(sp.region[w] + lay.q);
+        sc.dst[1][w] = reinterpret_cast<bf16*>(sp.region[w] + lay.k);
+        vdst[w] = reinterpret_cast<bf16*>(sp.region[w] + lay.v);
+      }
+      RUN(launch_rmsnorm_rope_stats(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), W_BF16(p + "attn1.norm_k.weight"), 2, h->rope_cos,
+                                    h->rope_sin, Lfull, c.attention_head_dim, ws.stats_qkv, 3 * tD, tD, s, &sc));
+      RUN(launch_sp_scatter_cols(ws.qkv + 2 * D, 3 * D, B, L, D, vdst, sp.world, Dl, Lfull, tok0, s));
+      RUN(launch_sp_barrier(sp, lay, s));
+      AttnArgs a;
+      a.B = B; a.H = Hl; a.Lq = Lfull; a.Lk = Lfull;
+      a.q = reinterpret_cast<const bf16*>(sp.region[sp.rank] + lay.q); a.ldq = Dl;
+      a.k = reinterpret_cast<const bf16*>(sp.region[sp.rank] + lay.k); a.ldk = Dl;
+      a.v = reinterpret_cast<const bf16*>(sp.region[sp.rank] + lay.v); a.ldv = Dl;
+      a.out = reinterpret_cast<bf16*>(sp.region[sp.rank] + lay.attn); a.ldo = D;
+      for (int w = 0; w < sp.world; ++w) a.out_peer[w] = reinterpret_cast<bf16*>(sp.region[w] + lay.attn);
+      a.peer_rows = L;
+      a.out_col0 = sp.rank * Dl;
+      a.scale = attn_scale;
+      RUN2(attention(h, a, s));
+      RUN(launch_sp_barrier(sp, lay, s));
+      attn_in = reinterpret_cast<const bf16*>(sp.region[sp.rank] + lay.attn);
+    } else {
     if (st) {
       RUNC(CAT_ROWS, 8.0 * M * D, launch_rmsnorm_rope_stats(ws.qkv, 3 * D, M, D, c.eps, W_BF16(p + "attn1.norm_q.weight"), W_BF16(p + "attn1.norm_k.weight"), 2,
                                                              h->rope_cos, h->rope_sin, L, c.attention_head_dim, ws.stats_qkv, 3 * tD, tD, s));
@@ -572,7 +645,8 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
       a.scale = attn_scale;
       RUN2(attention(h, a, s));
     }
-    RUN2(linear(h, ws.attn, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s, st ? ws.stats_x : nullptr, 1));
+    }
+    RUN2(linear(h, attn_in, D, p + "attn1.to_out.0", M, D, D, ws.x, D, EPI_BIAS_GATE_RESID, ws.x, D, mod + 2 * D, 6 * D, L, s, st ? ws.stats_x : nullptr, 1));
     // 2. cross-attention
     RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, nullptr, nullptr, 0, 0, W_F32(p + "norm2.weight"), W_F32(p + "norm2.bias"), 0));
     bf16* q2 = ws.qkv;  // [M, D]
@@ -622,6 +696,16 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
   // ---- output head (:451-467): modf = [B, 2, D] with shift = chunk 0, scale = chunk 1
   RUNC(CAT_ROWS, 4.0 * M * D, ln(ws.x, ws.xn, ws.modf + D, ws.modf, 2 * D, L, nullptr, nullptr, 1));
   RUN2(linear(h, ws.xn, D, "proj_out", M, No, D, ws.yout, No, EPI_BIAS, nullptr, 0, nullptr, 0, 1, s));
+  if (spx) {   // every rank gets the whole head output (rows all-gathered by peer stores), then un-patchifies the full sample
+    bf16* ydst[8];
+    for (int w = 0; w < sp.world; ++w) ydst[w] = reinterpret_cast<bf16*>(sp.region[w] + lay.yout);
+    RUN(launch_sp_broadcast_rows(ws.yout, B, L, No, ydst, sp.world, Lfull, tok0, s));
+    RUN(launch_sp_barrier(sp, lay, s));
+    RUN(launch_unpatchify(reinterpret_cast<const bf16*>(sp.region[sp.rank] + lay.yout), No, reinterpret_cast<bf16*>(sample), B, c.out_channels, frames,
+                          height, width, s));
+    RUN(launch_sp_barrier(sp, lay, s));   // nobody overwrites a peer's yout (next forward) before it has been read
+    return CE_OK;
+  }
   RUN(launch_unpatchify(ws.yout, No, reinterpret_cast<bf16*>(sample), B, c.out_channels, frames, height, width, s));
   return CE_OK;
 }

@@ -123,7 +123,7 @@ template <int HV>
 __global__ void __launch_bounds__(ROW_THREADS, 2)
 rmsnorm_rope_stats_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float eps, const bf16* __restrict__ weight0,
                           const bf16* __restrict__ weight1, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int L,
-                          int head_dim, const float2* __restrict__ stats, int stats_ld, int tiles) {
+                          int head_dim, const float2* __restrict__ stats, int stats_ld, int tiles, SpScatter sp) {
   const int lane64 = threadIdx.x & 63;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (ROW_THREADS / 64) + (threadIdx.x >> 6);
@@ -135,7 +135,7 @@ rmsnorm_rope_stats_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float 
   const int nvec = D >> 3;
   uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx + (size_t)mat * D);
   const uint4* wr = reinterpret_cast<const uint4*>(mat ? weight1 : weight0);
-  const int tok = rope_cos ? row % L : 0;
+  const int tok = sp.world ? sp.tok0 + row % sp.rows_per_batch : (rope_cos ? row % L : 0);   // global token (RoPE position)
   const int half = head_dim >> 1;
 #pragma unroll
   for (int i = 0; i < HV; ++i) {
@@ -146,8 +146,8 @@ rmsnorm_rope_stats_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float 
       unpack8(wr[idx], w);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round(f[j] * rstd) * w[j]);
+      const int c = idx * 8;
       if (rope_cos) {
-        const int c = idx * 8;
         const int pair0 = (c % head_dim) >> 1;
         const float4 cs = *reinterpret_cast<const float4*>(rope_cos + (size_t)tok * half + pair0);
         const float4 sn = *reinterpret_cast<const float4*>(rope_sin + (size_t)tok * half + pair0);
@@ -160,7 +160,14 @@ rmsnorm_rope_stats_kernel(bf16* __restrict__ x, int ldx, int rows, int D, float 
           o[2 * p + 1] = re * sv[p] + im * cv[p];
         }
       }
-      xr[idx] = pack8(o);
+      if (sp.world) {   // to the rank that owns this head (peer store)
+        const int head = c / head_dim, dr = head / sp.heads_per_rank, bi = row / sp.rows_per_batch;
+        bf16* d = sp.dst[mat][dr] + ((size_t)bi * sp.L_total + tok) * ((size_t)sp.heads_per_rank * head_dim) +
+                  (size_t)(head % sp.heads_per_rank) * head_dim + c % head_dim;
+        *reinterpret_cast<uint4*>(d) = pack8(o);
+      } else {
+        xr[idx] = pack8(o);
+      }
     }
   }
 }
@@ -480,14 +487,17 @@ int launch_layernorm_stats(const bf16* x, int ldx, bf16* y, int ldy, int rows, i
 
 int launch_rmsnorm_rope_stats(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight0, const bf16* weight1, int nmat,
                               const float* rope_cos, const float* rope_sin, int L, int head_dim, const float2* stats, int stats_ld, int tiles,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, const SpScatter* sp) {
   CE_REQUIRE(rows > 0 && D % 8 == 0 && D <= MAX_D && ldx % 8 == 0 && weight0 != nullptr, "rmsnorm(stats): shapes");
   CE_REQUIRE(nmat == 1 || (nmat == 2 && weight1 != nullptr), "rmsnorm(stats): one or two matrices");
   CE_REQUIRE(stats != nullptr && tiles >= 1 && tiles <= 32 && stats_ld >= nmat * tiles, "rmsnorm(stats): tile partials");
   if (rope_cos) CE_REQUIRE(rope_sin && L > 0 && head_dim % 8 == 0 && D % head_dim == 0, "rmsnorm(stats): rope table / head_dim");
   dim3 grid((rows + ROW_THREADS / 64 - 1) / (ROW_THREADS / 64), nmat);
   const int nvec = D / 8;
-#define CE_RMSS(V) rmsnorm_rope_stats_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight0, weight1, rope_cos, rope_sin, L, head_dim, stats, stats_ld, tiles)
+  SpScatter spv;
+  if (sp) spv = *sp;
+  if (spv.world) CE_REQUIRE(spv.world <= 8 && spv.heads_per_rank > 0 && spv.rows_per_batch > 0 && rows % spv.rows_per_batch == 0, "rmsnorm(stats): scatter");
+#define CE_RMSS(V) rmsnorm_rope_stats_kernel<V><<<grid, ROW_THREADS, 0, stream>>>(x, ldx, rows, D, eps, weight0, weight1, rope_cos, rope_sin, L, head_dim, stats, stats_ld, tiles, spv)
   if (nvec <= 128) CE_RMSS(2);
   else if (nvec <= 256) CE_RMSS(4);
   else if (nvec <= 640) CE_RMSS(10);

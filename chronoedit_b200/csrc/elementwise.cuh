@@ -26,9 +26,21 @@ int launch_rmsnorm_rope(bf16* x, int ldx, int rows, int D, float eps, const bf16
 int launch_layernorm_stats(const bf16* x, int ldx, bf16* y, int ldy, int rows, int D, float eps, const float* scale, const float* shift,
                            int mod_stride, int rows_per_batch, const float* weight, const float* bias, int scale_is_1p, const float2* stats,
                            int stats_ld, int tiles, int tile_n, cudaStream_t stream);
+// Sequence-parallel scatter of the normalised q | k (csrc/seqpar.cu): rows are the LOCAL tokens of this rank (rows_per_batch each,
+// global token = tok0 + local index), RoPE uses the global token, and instead of being written back in place the vector of head h
+// goes to the rank that owns head h:  dst[mat][h / heads_per_rank] + ((b * L_total + token) * (heads_per_rank * head_dim)
+// + (h % heads_per_rank) * head_dim + offset inside the head).
+struct SpScatter {
+  bf16* dst[2][8];
+  int world = 0;            // 0 = no scatter (in place)
+  int heads_per_rank = 0;
+  int L_total = 0;          // tokens per sample over all ranks
+  int rows_per_batch = 0;   // local tokens per sample
+  int tok0 = 0;             // first global token of this rank
+};
 int launch_rmsnorm_rope_stats(bf16* x, int ldx, int rows, int D, float eps, const bf16* weight0, const bf16* weight1, int nmat,
                               const float* rope_cos, const float* rope_sin, int L, int head_dim, const float2* stats, int stats_ld, int tiles,
-                              cudaStream_t stream);
+                              cudaStream_t stream, const SpScatter* sp = nullptr);
 
 // patches[(b,f,i,j), c*4 + dh*2 + dw] = x[b, c, f, 2i+dh, 2j+dw]   (im2row for the k=s=(1,2,2) patch-embedding conv, :368,429-430)
 int launch_patchify(const bf16* x, bf16* patches, int B, int C, int T, int H, int W, cudaStream_t stream);

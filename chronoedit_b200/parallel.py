@@ -88,3 +88,76 @@ def gather_objects(local: Sequence, dst: int = 0):
     out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
     dist.gather_object(list(local), out, dst=dst)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Sequence parallelism for single-edit latency
+# ----------------------------------------------------------------------------------------------------------------------
+def enable_sequence_parallel(model, batch: int, frames: int, height: int, width: int, group=None) -> int:
+    """Split the tokens of ONE edit over the ranks of `group` (one process per GPU of a node; reference: the Ulysses path of
+    chronoedit_diffsynth/wan_video_new_chronoedit.py:330-355 and the TE ring of chronoedit/_src/networks/wan2pt1.py:352-353).
+
+    Allocates this rank's peer region (ce_ipc_alloc), exchanges the 64-byte CUDA IPC handles through torch.distributed (plumbing
+    only), opens the peers' regions and hands the pointer table to the C handle (ce_dit_sp_configure).  From then on
+    `model(hidden_states, timestep, encoder_hidden_states, encoder_hidden_states_image)` -- called with the SAME full inputs on every
+    rank -- computes 1/world of the tokens per rank, exchanges q/k/v and the attention output by peer stores over NVLink inside the
+    kernels (no collective call on the data path), and returns the same full sample on every rank, bit-identical to the single-GPU
+    forward.  Geometry-specific: call again for another latent shape.  Returns the region size in bytes."""
+    import ctypes
+
+    from . import _lib
+    from ._lib import CEError, check
+
+    if not dist.is_initialized():
+        raise CEError("enable_sequence_parallel needs an initialised torch.distributed process group (one process per GPU)")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    L = _lib.lib()
+    if not model._packed:
+        model.pack_weights()
+    disable_sequence_parallel(model)
+    if world == 1:
+        return 0
+    n = L.ce_dit_sp_region_bytes(model._handle, batch, frames, height, width, world)
+    if n < 0:
+        raise CEError(f"sequence parallel: tokens and heads must be divisible by the world size {world}")
+    with torch.cuda.device(model.device):
+        own = ctypes.c_void_p()
+        check(L.ce_ipc_alloc(n, ctypes.byref(own)))
+        hbuf = (ctypes.c_uint8 * 64)()
+        check(L.ce_ipc_get_handle(own, hbuf))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(hbuf), group=group)
+        ptrs, opened = [], []
+        for w in range(world):
+            if w == rank:
+                ptrs.append(own.value)
+                continue
+            p = ctypes.c_void_p()
+            hb = (ctypes.c_uint8 * 64).from_buffer_copy(handles[w])
+            check(L.ce_ipc_open(hb, ctypes.byref(p)))
+            ptrs.append(p.value)
+            opened.append(p)
+        table = (ctypes.c_void_p * world)(*ptrs)
+        check(L.ce_dit_sp_configure(model._handle, rank, world, table, n))
+        torch.cuda.synchronize(model.device)
+    dist.barrier(group=group)   # every region exists, is zeroed and is mapped everywhere before the first flag is written
+    model._sp_state = {"own": own, "opened": opened, "world": world, "bytes": n}
+    model._graphs = {}
+    return int(n)
+
+
+def disable_sequence_parallel(model) -> None:
+    from . import _lib
+
+    st = getattr(model, "_sp_state", None)
+    if not st:
+        return
+    L = _lib.lib()
+    torch.cuda.synchronize(model.device)
+    L.ce_dit_sp_configure(model._handle, 0, 1, None, 0)
+    for p in st["opened"]:
+        L.ce_ipc_close(p)
+    if dist.is_initialized():
+        dist.barrier()
+    L.ce_ipc_free(st["own"])
+    model._sp_state = None

@@ -98,6 +98,25 @@ int ce_dit_forward_ex(ce_dit* h, const void* hidden_states, const float* timeste
                       int text_len, void* workspace, int64_t workspace_bytes, void* block0_out, void* ctx_cache,
                       int64_t ctx_cache_bytes, int ctx_reuse, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Sequence parallelism over the GPUs of one node for single-edit latency (reference: the Ulysses /
+ * xfuser path chronoedit_diffsynth/wan_video_new_chronoedit.py:330-355, 1448-1498 and the TE ring of
+ * chronoedit/_src/networks/wan2pt1.py:352-353, 917-941).  One process per GPU, all weights on every rank, the tokens of the edit
+ * split into `world` contiguous ranges.  The heads <-> tokens exchange around the self-attention is done by the producing kernels
+ * themselves with stores into the consumer's memory over NVLink (csrc/seqpar.cuh); phases are ordered by a flag barrier in peer
+ * memory.  Every rank passes the SAME full inputs and receives the same full sample, bit-identical to the single-GPU forward.
+ *   region: one device buffer of ce_dit_sp_region_bytes(...) per rank, allocated with ce_ipc_alloc (zeroed), shared with the peers
+ *   through ce_ipc_get_handle / ce_ipc_open (CUDA IPC; the 64-byte handles travel by any host channel, e.g. torch.distributed);
+ *   region_ptrs[w] = address of rank w's region in THIS process.  world = 1 switches it off.
+ * ------------------------------------------------------------------------------------------------------------ */
+int64_t ce_dit_sp_region_bytes(const ce_dit* h, int batch, int frames, int height, int width, int world);
+int ce_dit_sp_configure(ce_dit* h, int rank, int world, void* const* region_ptrs, int64_t region_bytes);
+int ce_ipc_alloc(int64_t bytes, void** ptr);
+int ce_ipc_free(void* ptr);
+int ce_ipc_get_handle(void* ptr, void* handle_out_64_bytes);
+int ce_ipc_open(const void* handle_64_bytes, void** ptr);
+int ce_ipc_close(void* ptr);
+
 /* Parity aid: from now on every forward copies the output of block layers[i] ([B*L, D] bf16) to dst[i] (n = 0 clears). */
 int ce_dit_set_capture(ce_dit* h, const int32_t* layers, void* const* dst, int n);
 
