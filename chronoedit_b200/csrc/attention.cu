@@ -147,27 +147,43 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0);   // Q (K-major) x K^T (K-major)
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 1);  // P (K-major) x V (MN-major)
-      uint64_t dq[8], dkk[2][8], dp[2][8], dvv[2][8];
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        dq[kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::q) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          dkk[g][kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::k + g * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          dp[g][kk] = umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::p + g * TILE_BYTES) + (kk >> 2) * HALF_BYTES) + 2 * (kk & 3);
-          dvv[g][kk] = umma_desc_mnmajor_sw128(smem_u32(smem + SmemLayout::v + g * TILE_BYTES) + kk * 2048, HALF_BYTES);
-        }
-      }
+      // Descriptors are rebuilt from one base word per operand right before each batch of MMAs (a few integer adds ahead of the asm
+      // statement, nothing between the MMAs).  Keeping all 56 of them live spilled them to local memory in this 80-register warp, and a
+      // reload is an L2 round trip on the critical chain (local memory does not stay in what is left of L1 next to 200+ KB of shared
+      // memory): measured on attention6.cu, 400-500 cycles per key tile (profiles/r2s_attention6_event_log.log).
+      const uint32_t hi_k = uint32_t(umma_desc_kmajor_sw128(0) >> 32), hi_v = uint32_t(umma_desc_mnmajor_sw128(0, HALF_BYTES) >> 32);
+      auto desc = [](uint32_t lo, uint32_t hi) { return (uint64_t(hi) << 32) | lo; };
+      const uint32_t q_lo = uint32_t(umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::q)));
+      const uint32_t k_lo = uint32_t(umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::k)));
+      const uint32_t p_lo = uint32_t(umma_desc_kmajor_sw128(smem_u32(smem + SmemLayout::p)));
+      const uint32_t v_lo = uint32_t(umma_desc_mnmajor_sw128(smem_u32(smem + SmemLayout::v), HALF_BYTES));
       auto issue_s = [&](int g, int t) {
         mbar_wait(&bars[K_FULL + g], t & 1, 30 + g);
         tc_fence_after();
-        umma_bf16_ss_x8(tmem_base + g * 128, dq, dkk[g], IDESC_S, 0);
+        uint32_t qb = q_lo, kb = k_lo + g * (TILE_BYTES >> 4);
+        asm volatile("" : "+r"(qb), "+r"(kb));   // opaque: nothing is carried (= spilled) from one batch to the next
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * (HALF_BYTES >> 4) + 2 * (kk & 3);
+          da[kk] = desc(qb + off, hi_k);
+          db[kk] = desc(kb + off, hi_k);
+        }
+        umma_bf16_ss_x8(tmem_base + g * 128, da, db, IDESC_S, 0);
         umma_commit(&bars[K_EMPTY + g]);
         umma_commit(&bars[S_FULL + g]);
       };
       auto issue_pv = [&](int g, int t) {
         tc_fence_after();
-        umma_bf16_ss_x8(tmem_base + 256 + g * 128, dp[g], dvv[g], IDESC_PV, t != 0);
+        uint32_t pb = p_lo + g * (TILE_BYTES >> 4), vb = v_lo + g * (TILE_BYTES >> 4);
+        asm volatile("" : "+r"(pb), "+r"(vb));
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          da[kk] = desc(pb + (kk >> 2) * (HALF_BYTES >> 4) + 2 * (kk & 3), hi_k);
+          db[kk] = desc(vb + kk * (2048 >> 4), hi_v);
+        }
+        umma_bf16_ss_x8(tmem_base + 256 + g * 128, da, db, IDESC_PV, t != 0);
         umma_commit(&bars[V_EMPTY + g]);
         umma_commit(&bars[PV_DONE + g]);
       };
@@ -416,9 +432,11 @@ int make_qkv_tmap(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld)
 
 int launch_attention2(const AttnArgs& a, cudaStream_t stream);  // attention2.cu
 int launch_attention5(const AttnArgs& a, cudaStream_t stream);  // attention5.cu
+int launch_attention6(const AttnArgs& a, cudaStream_t stream);  // attention6.cu
 
-// Which kernel serves long single-source problems (the self-attention): 2 = attention2.cu (default), 5 = attention5.cu
-// (cta_group::2, experimental), 0 = this file's kernel for everything.  CE_ATTN_V2 in the environment, or
+// Which kernel serves long single-source problems (the self-attention): 6 = attention6.cu (two softmax threads per row; default:
+// +6 % isolated, +5.8 % inside the step over attention2.cu, profiles/r2u_*, r2v_*), 2 = attention2.cu (one thread per row),
+// 5 = attention5.cu (cta_group::2, experimental), 0 = this file's kernel for everything.  CE_ATTN_V2 in the environment, or
 // ce_debug_attention_kernel() at run time (tests exercise the non-default kernels through it).
 static int g_attn_override = -1;
 void set_attention_kernel(int v) { g_attn_override = v; }
@@ -426,7 +444,7 @@ static int attn_version() {
   if (g_attn_override >= 0) return g_attn_override;
   static const int v = [] {
     const char* e = getenv("CE_ATTN_V2");
-    return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : 2));
+    return !e ? 6 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : (e[0] == '2' ? 2 : 6)));
   }();
   return v;
 }
@@ -435,7 +453,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty problem");
   // long single-source problems (the self-attention): two query tiles per CTA sharing every K/V tile, P in TMEM
   if (a.Lk2 == 0 && !a.accumulate && a.Lq >= 256 && a.Lk >= 256 && a.head_dim == HD && attn_version() != 0)
-    return (attn_version() == 5 && a.peer_rows == 0) ? launch_attention5(a, stream) : launch_attention2(a, stream);
+    return (attn_version() == 5 && a.peer_rows == 0) ? launch_attention5(a, stream)
+           : attn_version() == 2                     ? launch_attention2(a, stream)
+                                                     : launch_attention6(a, stream);
   CE_REQUIRE(a.peer_rows == 0, "attention: the sequence-parallel output scatter is built into the self-attention kernel (attention2.cu) only");
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");

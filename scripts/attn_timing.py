@@ -8,7 +8,7 @@ B, H, Lq = 1, 40, 7200
 D = H * 128
 x = torch.randn(B, Lq, 3 * D, device="cuda", dtype=torch.bfloat16)
 out = torch.empty(B, Lq, D, device="cuda", dtype=torch.bfloat16)
-buf = torch.zeros(256, dtype=torch.int64, device="cuda")
+buf = torch.zeros(512, dtype=torch.int64, device="cuda")
 L.check(lib.ce_debug_attention_timing(L.ptr(buf)))
 for _ in range(3):
     L.check(lib.ce_attention_bf16(L.ptr(x), 3 * D, L.ptr(x[..., D:]), 3 * D, L.ptr(x[..., 2 * D:]), 3 * D, L.ptr(out), D, B, H, Lq, Lq, 1 / math.sqrt(128), 0,
@@ -16,6 +16,20 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = buf.cpu().tolist()
 ver = os.environ.get("CE_ATTN_V2", "2")
+if ver == "6":
+    # attention6.cu: event log only (block 0, key tiles 16..23): per query tile and half-row thread
+    t0 = t[64]
+    print("kernel: attention6 (two softmax threads per row); cycles relative to 'S(16) seen' by tile 0 / half 0")
+    for qt in range(2):
+        for hf in range(2):
+            print(f"query tile {qt}, half {hf}:  j | S seen | S in regs | max exchanged | first P part | last P part" + (" || first P.V issued | last P.V issued | S(j+1) issued" if hf == 0 else ""))
+            for k in range(8):
+                e = t[64 + qt * 128 + hf * 64 + 8 * k: 64 + qt * 128 + hf * 64 + 8 * k + 8]
+                line = "  j=%d  %7d %7d %7d %7d %7d" % (16 + k, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0)
+                if hf == 0:
+                    line += " || %7d %7d %7d" % (e[5] - t0, e[6] - t0, e[7] - t0)
+                print(line)
+    sys.exit(0)
 v2 = ver != "0"
 names = (["wait S", "ld S + free buffer", "max", "wait m(j-1), decide, publish m(j)", "(rescale)", "wait exp turn, exp, wait P.V(j-2)", "store P, arrive"] if ver == "5" else
          ["wait S", "ld S", "max", "rescale, exp of keys 0-79, publish P[0:64)", "exp of keys 80-127, publish P[64:128)"]) if v2 else ["wait S", "ld S", "max+decide", "exp+pack", "wait PV(t-1)/rescale", "store P + arrive"]

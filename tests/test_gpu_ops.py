@@ -185,9 +185,9 @@ def _rows_sum_property():
 
 
 @gpu
-@pytest.mark.parametrize("version", [5, 0])
+@pytest.mark.parametrize("version", [2, 5, 0])
 def test_attention_alternative_kernels(version):
-    """The non-default self-attention kernels (5: cta_group::2 cluster kernel with two softmax groups feeding one accumulator,
+    """The non-default self-attention kernels (2: one softmax thread per score row, 5: cta_group::2 cluster kernel with two softmax groups feeding one accumulator,
     0: single-tile kernel) against the same oracle comparisons and the full-size row-sum property -- the latter has thousands of
     lazy-rescale events (scores scaled x2), which is what exercises the shared-running-max protocol of kernel 5."""
     L = _lib()
