@@ -270,11 +270,21 @@ def test_rmsnorm_rope(rows, H, rope):
 
 
 @gpu
-@pytest.mark.parametrize("Lq,Lk,Lk2", [(300, 512, 257), (7200, 512, 257), (130, 7, 300)])
-def test_attention_dual_source(Lq, Lk, Lk2):
-    """text + image cross-attention in one launch == sum of two separate bf16 SDPAs (transformer_chronoedit.py:84-104)."""
+@pytest.mark.parametrize("Lq,Lk,Lk2,version", [(300, 512, 257, -1), (7200, 512, 257, -1), (130, 7, 300, -1), (300, 7, 300, 7), (513, 640, 129, 7),
+                                               (7200, 512, 257, 7)])
+def test_attention_dual_source(Lq, Lk, Lk2, version):
+    """text + image cross-attention in one launch == sum of two separate bf16 SDPAs (transformer_chronoedit.py:84-104).  Default:
+    attention.cu's two-group kernel; version 7: attention6.cu's two-source mode (the sources one after the other in a 256-query CTA)."""
     L = _lib()
     lib = L.lib()
+    L.check(lib.ce_debug_attention_kernel(version))
+    try:
+        _run_attention_dual(L, lib, Lq, Lk, Lk2)
+    finally:
+        L.check(lib.ce_debug_attention_kernel(-1))
+
+
+def _run_attention_dual(L, lib, Lq, Lk, Lk2):
     B, H, hd = 2, 2, 128
     D = H * hd
     g = torch.Generator(device="cpu").manual_seed(Lq + Lk2)
