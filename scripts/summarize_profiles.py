@@ -6,8 +6,8 @@ import csv, json, os, subprocess, sys, collections
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 os.makedirs("profiles", exist_ok=True)
 # 1. launch list: per-kernel total time / count / share
-path = f"gpurun_out/launches_{tag}.csv"
-if os.path.exists(path):
+for path, outp in ((f"gpurun_out/launches_{tag}.csv", f"profiles/{tag}_launches_summary.csv"), (f"gpurun_out/launches_vae_{tag}.csv", f"profiles/{tag}_launches_vae_summary.csv")):
+  if os.path.exists(path):
     rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("=="))]
     hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value"); ui = hdr.index("Metric Unit")
     agg = collections.OrderedDict()
@@ -18,16 +18,17 @@ if os.path.exists(path):
         ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(u, 1)
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ns
     tot = sum(a[1] for a in agg.values())
-    with open(f"profiles/{tag}_launches_summary.csv", "w") as f:
+    with open(outp, "w") as f:
         f.write("kernel,launches,total_us,share\n")
         for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"\"{k}\",{n},{ns/1e3:.1f},{ns/tot:.4f}\n")
-    print(open(f"profiles/{tag}_launches_summary.csv").read())
+    print(open(outp).read())
 # 2. full captures: selected metrics per captured launch
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "smsp__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_tensor.sum"]
+        "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "smsp__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_tensor.sum",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__m_xbar2l1tex_read_bytes.sum"]
 for k in ("gemm", "attn", "xattn", "rows", "conv"):
     rep = f"gpurun_out/prof_{k}_{tag}.ncu-rep"
     if not os.path.exists(rep): continue
