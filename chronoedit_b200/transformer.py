@@ -398,7 +398,8 @@ class ChronoEditTransformer3DModel(nn.Module):
         caps: Dict[int, torch.Tensor] = {}
         if capture_layers:
             caps = {int(l): torch.empty(B * L_tok, Dm, dtype=torch.bfloat16, device=dev) for l in capture_layers}
-        if self.use_cuda_graph and not caps and b0 is None:
+        # (no graph replay in sequence-parallel mode: the peer barrier's epoch is a launch argument and must advance every forward)
+        if self.use_cuda_graph and not caps and b0 is None and not getattr(self, "_sp_state", None):
             out = self._graphed_forward(x, t, txt, img, encoder_hidden_states, encoder_hidden_states_image)
         else:
             self._native_forward(x, t, txt, img, out, b0, caps, encoder_hidden_states, encoder_hidden_states_image)
