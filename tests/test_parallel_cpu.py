@@ -67,3 +67,16 @@ def test_weight_broadcast_and_sharding_gloo_world2():
     assert f0 == f1, "weights differ across ranks after the broadcast"
     assert sorted(e0 + e1) == [0, 1, 2, 3, 4] and e0 == [0, 2, 4] and e1 == [1, 3]
     assert n0 == x0 and n1 == x1, "broadcast byte count must equal the parameter bytes"
+
+
+def test_sequence_parallel_host_checks():
+    """enable_sequence_parallel fails loudly (never silently falls back to a single-GPU forward) without a process group, and the
+    region-size query rejects a missing handle; the data path itself needs NVLink peers (tests/test_gpu_seqpar.py, 2 GPUs)."""
+    from chronoedit_b200 import _lib
+    from chronoedit_b200._lib import CEError
+
+    assert not dist.is_initialized()
+    with pytest.raises(CEError, match="process group"):
+        parallel.enable_sequence_parallel(object(), 1, 2, 4, 4)
+    assert _lib.lib().ce_dit_sp_region_bytes(None, 1, 2, 4, 4, 2) == -1
+    parallel.disable_sequence_parallel(object())   # a model that never enabled it: no-op
