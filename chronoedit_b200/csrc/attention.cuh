@@ -34,6 +34,6 @@ struct AttnArgs {
 };
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
-void set_attention_kernel(int version);  // -1 default / environment, 0, 2, 5 (see attention.cu)
+void set_attention_kernel(int version);  // -1 default / environment, 0, 2, 5, 6, 7 (see attention.cu)
 
 }  // namespace ce

@@ -1,10 +1,12 @@
 // Self-attention forward, second generation: TWO 128-query tiles per CTA share every K/V tile, P lives in TMEM.
+// (Round-1 kernel with the round-2 issue path; attention6.cu -- two softmax threads per score row -- is the default now, this one
+// stays selectable with CE_ATTN_V2=2 / ce_debug_attention_kernel(2) and is covered by the same tests.)
 //
 //   out[b, i, h*128:(h+1)*128] = softmax_j( q[b,i,h,:] . k[b,j,h,:] * scale ) @ v[b,j,h,:]          (head_dim 128)
 //
 // One CTA per (256 queries, head, batch); 384 threads = 3 warpgroups (setmaxnreg 80 / 208 / 208):
 //   warp 0        TMA producer: Q0, Q1 once; K tiles through a 3-deep ring, V tiles through a 2-deep ring (128 keys each)
-//   warp 1        MMA issuer (one thread, event-driven): S_q = Q_q K_j^T (SS)  and  O_q += P_q V_j (TS: P read from TMEM,
+//   warp 1        MMA issuer (one elected thread, fixed order, see below): S_q = Q_q K_j^T (SS)  and  O_q += P_q V_j (TS: P read from TMEM,
 //                 V consumed as an MN-major B operand straight from the row-major tile)
 //   warps 4-7     softmax group 0 = query tile 0,   warps 8-11 softmax group 1 = query tile 1: ordinary online softmax over
 //                 ALL key tiles (running max / sum in registers, lazy rescale of O), P written back as packed bf16 into the
