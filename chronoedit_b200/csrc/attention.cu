@@ -444,7 +444,7 @@ static int attn_version() {
   if (g_attn_override >= 0) return g_attn_override;
   static const int v = [] {
     const char* e = getenv("CE_ATTN_V2");
-    return !e ? 6 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : (e[0] == '2' ? 2 : (e[0] == '7' ? 7 : 6))));
+    return !e ? 6 : (e[0] == '0' ? 0 : (e[0] == '5' ? 5 : (e[0] == '2' ? 2 : 6)));
   }();
   return v;
 }
@@ -456,10 +456,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     return (attn_version() == 5 && a.peer_rows == 0) ? launch_attention5(a, stream)
            : attn_version() == 2                     ? launch_attention2(a, stream)
                                                      : launch_attention6(a, stream);
-  // version 7 (A/B only): the two-source cross-attention through attention6.cu too, the second source following the first in the same
-  // CTA.  Measured slower than this file's two-group kernel (0.439 vs 0.405 ms at 7200 x (512 + 257), profiles/r2x_*): with 7 key
-  // tiles per CTA the serial per-tile chain and the unoverlapped prologue / epilogue of a 256-query CTA outweigh the shared K/V tiles.
-  if (a.Lk2 > 0 && !a.accumulate && a.Lq >= 256 && a.head_dim == HD && a.peer_rows == 0 && attn_version() == 7) return launch_attention6(a, stream);
+  // The two-source cross-attention stays with this file's two-group kernel.  Two re-builds on attention6.cu's machinery were
+  // measured and dropped (patches + logs under profiles/): the sources one after the other in a 256-query CTA (0.439 ms, r2x) and
+  // one stream per source over a 128-query tile, started together or staggered (0.495 / 0.513 ms, r2I / r2J) against 0.405 ms here:
+  // with 4 + 3 key tiles per CTA the fixed cost of a 640-thread CTA outweighs the faster softmax.
   CE_REQUIRE(a.peer_rows == 0, "attention: the sequence-parallel output scatter is built into the self-attention kernel (attention2.cu) only");
   CE_REQUIRE(a.head_dim == HD, "attention: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dims % 8");

@@ -51,15 +51,10 @@ enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + NK, V_FULL = K_EMPTY + NK, V_E
 
 // POLY8 of every 8 exp2 pairs run on the FMA pipe (f2_exp2_poly).  SPLIT: 0 = each half publishes its 64 keys of P at once; 16 / 24 = in
 // two parts, the first after SPLIT exp2 pairs (32 + 32 or 48 + 16 keys): the shorter the last part, the less P.V sits in the serial chain.
-// DUAL: a second key/value source follows the first in the same CTA (text, then image keys of the cross-attention,
-// transformer_chronoedit.py:84-104): an independent softmax per source -- at the first key tile of the second source every thread
-// normalises its part of O, stores it as bf16, and starts over (new running maximum, row sum 0, first P.V overwrites O); the
-// epilogue adds the two bf16 results the way the reference adds the two SDPA outputs (:103-104).
-template <int POLY8, int SPLIT, bool TIMED, bool DUAL>
+template <int POLY8, int SPLIT, bool TIMED>
 __global__ void __launch_bounds__(ATTN6_THREADS, 1)
 attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                      const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_k2,
-                      const __grid_constant__ CUtensorMap tma_v2, AttnArgs a) {
+                      const __grid_constant__ CUtensorMap tma_v, AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem6::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS6);
@@ -70,8 +65,7 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const int q0 = blockIdx.x * 2 * BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int n1 = (a.Lk + BKV - 1) / BKV;                               // key tiles of the first source
-  const int n_tiles = n1 + (DUAL ? (a.Lk2 + BKV - 1) / BKV : 0);       // ... and of both
+  const int n_tiles = (a.Lk + BKV - 1) / BKV;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -83,10 +77,6 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
-    if (DUAL) {
-      tma_prefetch_desc(&tma_k2);
-      tma_prefetch_desc(&tma_v2);
-    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -112,10 +102,9 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           tma_load_3d(smem + Smem6::q + qt * TILE_BYTES + HALF_BYTES, &tma_q, &bars[Q_FULL], h * HD + 64, q0 + qt * BQ, b);
         }
         for (int t = 0; t < n_tiles; ++t) {
-          const bool second = DUAL && t >= n1;
-          const CUtensorMap* mk = second ? &tma_k2 : &tma_k;
-          const CUtensorMap* mv = second ? &tma_v2 : &tma_v;
-          const int key0 = (second ? t - n1 : t) * BKV;
+          const CUtensorMap* mk = &tma_k;
+          const CUtensorMap* mv = &tma_v;
+          const int key0 = t * BKV;
           {
             const int st = t % NK;
             mbar_wait(&bars[K_EMPTY + st], ((t / NK) & 1) ^ 1, 10 + st);
@@ -170,7 +159,7 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         issue_s(1, 0);
         for (int j = 0; j < n_tiles; ++j) {
           const uint32_t vb0 = v_lo0 + (j % NV) * (TILE_BYTES >> 4);   // V(j): K-step kk starts 2048 bytes (16 keys x 128 B) further on
-          const bool fresh = j == 0 || (DUAL && j == n1);              // first key tile of a source: the first P.V overwrites O
+          const bool fresh = j == 0;                                   // the first P.V overwrites O
 #pragma unroll
           for (int qt = 0; qt < 2; ++qt) {
             const uint32_t p_tmem = tmem_base + qt * 128;   // packed bf16: 8 columns per K=16 step
@@ -231,39 +220,9 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const bool timed = timed_blk && quad == 0 && lane == 0;
 
     for (int j = 0; j < n_tiles; ++j) {
-      const bool second = DUAL && j >= n1;
-      const int valid = (second ? a.Lk2 - (j - n1) * BKV : a.Lk - j * BKV) - hf * 64;   // keys of this half that exist (may be <= 0)
+      const int valid = a.Lk - j * BKV - hf * 64;   // keys of this half that exist (may be <= 0 in the last tile)
       mbar_wait(&bars[S_FULL + qt], j & 1, 60 + qt);
       tc_fence_after();
-      if (DUAL && j == n1) {
-        // S(n1) ready implies P.V(n1-1) complete (in-order pipe): O holds the finished first source.  Normalise, park it in `out`
-        // as bf16 (this thread reads its own stores back in the epilogue), start the second softmax from scratch.
-        xs[hf * 128 + r] = l;
-        named_bar_sync(1 + qt * 4 + quad, 64);
-        const float inv1 = 1.0f / (xs[r] + xs[128 + r]);
-        named_bar_sync(1 + qt * 4 + quad, 64);   // both have read the sums before the slot carries a maximum again
-        const int row1 = q0 + qt * BQ + r;
-        bf16* o1 = a.out + ((size_t)b * a.Lq + row1) * a.ldo + h * HD + hf * 64;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(o_tmem + c * 32, o);
-          tmem_ld_wait();
-          if (row1 < a.Lq) {
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              float y[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[v4 * 8 + i]) * inv1;
-              *reinterpret_cast<uint4*>(o1 + c * 32 + v4 * 8) =
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-            }
-          }
-        }
-        tc_fence_before();
-        m = -INFINITY;
-        l = 0.f;
-      }
       CE_EVT6(timed, qt, hf, j, 0)
       uint32_t s[64];
       uint32_t pk[32];
@@ -290,7 +249,7 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       CE_EVT6(timed, qt, hf, j, 2)
       float alpha = 1.0f;
       bool need = false;
-      if (j == 0 || (DUAL && j == n1)) {
+      if (j == 0) {
         m = mx;
       } else {
         need = mx > m + RESCALE_THRESHOLD;
@@ -384,19 +343,8 @@ attention6_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           float y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[v4 * 8 + i]) * inv;
-          uint4 w = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-          if (DUAL) {   // + the first source's bf16 result: bf16(float(a) + float(b)), as torch adds two bf16 tensors
-            const uint4 f = *reinterpret_cast<const uint4*>(orow + c * 32 + v4 * 8);
-            const uint32_t fw[4] = {f.x, f.y, f.z, f.w}, sw[4] = {w.x, w.y, w.z, w.w};
-            uint32_t rw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 u = unpack_bf16x2(fw[i]), t2 = unpack_bf16x2(sw[i]);
-              rw[i] = pack_bf16x2(u.x + t2.x, u.y + t2.y);
-            }
-            w = make_uint4(rw[0], rw[1], rw[2], rw[3]);
-          }
-          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = w;
+          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) =
+              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
         }
       }
     }
@@ -418,8 +366,7 @@ int make_qkv_tmap6(CUtensorMap* m, const bf16* base, int B, int L, int H, int ld
 }  // namespace
 
 int launch_attention6(const AttnArgs& a, cudaStream_t stream) {
-  CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && a.Lk2 >= 0 && a.accumulate == 0, "attention6: no accumulate");
-  CE_REQUIRE(a.Lk2 == 0 || (a.k2 && a.v2 && a.peer_rows == 0 && a.ldk2 % 8 == 0 && a.ldv2 % 8 == 0), "attention6: second source arguments");
+  CE_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && a.Lk2 == 0 && a.accumulate == 0, "attention6: single source, no accumulate");
   CE_REQUIRE(a.peer_rows == 0 || (a.Lq + a.peer_rows - 1) / a.peer_rows <= 8, "attention6: at most 8 sequence-parallel peers");
   CE_REQUIRE(a.head_dim == HD, "attention6: only head_dim 128 is built");
   CE_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention6: leading dims % 8");
@@ -428,11 +375,6 @@ int launch_attention6(const AttnArgs& a, cudaStream_t stream) {
   if ((rc = make_qkv_tmap6(&tq, a.q, a.B, a.Lq, a.H, a.ldq))) return rc;
   if ((rc = make_qkv_tmap6(&tk, a.k, a.B, a.Lk, a.H, a.ldk))) return rc;
   if ((rc = make_qkv_tmap6(&tv, a.v, a.B, a.Lk, a.H, a.ldv))) return rc;
-  CUtensorMap tk2 = tk, tv2 = tv;
-  if (a.Lk2 > 0) {
-    if ((rc = make_qkv_tmap6(&tk2, a.k2, a.B, a.Lk2, a.H, a.ldk2))) return rc;
-    if ((rc = make_qkv_tmap6(&tv2, a.v2, a.B, a.Lk2, a.H, a.ldv2))) return rc;
-  }
   // developer knobs: CE_ATTN6_POLY (0..3 of every 8 exp2 pairs on the FMA pipe), CE_ATTN6_SPLIT (0, 16, 24: see the template comment)
   static const int poly = [] {
     const char* e = getenv("CE_ATTN6_POLY");
@@ -445,22 +387,20 @@ int launch_attention6(const AttnArgs& a, cudaStream_t stream) {
     return v == 0 ? 0 : (v == 24 ? 24 : 16);
   }();
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-#define CE_LAUNCH_ATTN6(P, SP, T, D)                                                                                \
-  do {                                                                                                              \
-    CE_ENSURE_SMEM((attention6_fwd_kernel<P, SP, T, D>), Smem6::total);                                             \
-    attention6_fwd_kernel<P, SP, T, D><<<grid, ATTN6_THREADS, Smem6::total, stream>>>(tq, tk, tv, tk2, tv2, a);      \
+#define CE_LAUNCH_ATTN6(P, SP, T)                                                                   \
+  do {                                                                                                \
+    CE_ENSURE_SMEM((attention6_fwd_kernel<P, SP, T>), Smem6::total);                                  \
+    attention6_fwd_kernel<P, SP, T><<<grid, ATTN6_THREADS, Smem6::total, stream>>>(tq, tk, tv, a);     \
   } while (0)
-#define CE_LAUNCH_ATTN6_S(SP)                                \
-  switch (poly) {                                            \
-    case 0: CE_LAUNCH_ATTN6(0, SP, false, false); break;     \
-    case 1: CE_LAUNCH_ATTN6(1, SP, false, false); break;     \
-    case 2: CE_LAUNCH_ATTN6(2, SP, false, false); break;     \
-    default: CE_LAUNCH_ATTN6(3, SP, false, false); break;    \
+#define CE_LAUNCH_ATTN6_S(SP)                         \
+  switch (poly) {                                     \
+    case 0: CE_LAUNCH_ATTN6(0, SP, false); break;     \
+    case 1: CE_LAUNCH_ATTN6(1, SP, false); break;     \
+    case 2: CE_LAUNCH_ATTN6(2, SP, false); break;     \
+    default: CE_LAUNCH_ATTN6(3, SP, false); break;    \
   }
-  if (a.Lk2 > 0) {
-    CE_LAUNCH_ATTN6(1, 16, false, true);     // the two-source cross-attention: built at the default knobs only
-  } else if (a.timing) {
-    if (split == 24) CE_LAUNCH_ATTN6(1, 24, true, false); else CE_LAUNCH_ATTN6(1, 16, true, false);   // event log: POLY 1 only
+  if (a.timing) {
+    if (split == 24) CE_LAUNCH_ATTN6(1, 24, true); else CE_LAUNCH_ATTN6(1, 16, true);   // event log: POLY 1 only
   } else if (split == 0) {
     CE_LAUNCH_ATTN6_S(0)
   } else if (split == 24) {

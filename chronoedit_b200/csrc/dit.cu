@@ -800,11 +800,10 @@ int ce_debug_attention_timing(long long* buf) {
 }
 
 // Test / A-B aid: which kernel serves the self-attention from now on (6 default = attention6.cu, 2 = attention2.cu, 5 cta_group::2
-// cluster kernel, 0 the single-tile kernel of attention.cu, 7 = 6 plus the two-source cross-attention through attention6.cu;
-// -1 back to the CE_ATTN_V2 / built-in default).
+// cluster kernel, 0 the single-tile kernel of attention.cu; -1 back to the CE_ATTN_V2 / built-in default).
 int ce_debug_attention_kernel(int version) {
-  if (version != -1 && version != 0 && version != 2 && version != 5 && version != 6 && version != 7)
-    return ce::fail(ce::CE_ERR_INVALID, "attention kernel version must be -1, 0, 2, 5, 6 or 7");
+  if (version != -1 && version != 0 && version != 2 && version != 5 && version != 6)
+    return ce::fail(ce::CE_ERR_INVALID, "attention kernel version must be -1, 0, 2, 5 or 6");
   ce::set_attention_kernel(version);
   return CE_OK;
 }

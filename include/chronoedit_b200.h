@@ -263,8 +263,7 @@ int ce_debug_attention_timing(long long* buf);
 
 /* Test / A-B aid: select the kernel that serves long single-source (self-)attention from now on: 6 = two query tiles per CTA, two
  * softmax threads per score row (default), 2 = two query tiles per CTA, one thread per row, 5 = cta_group::2 cluster kernel
- * (experimental), 0 = single-tile kernel, 7 = 6 and the two-source cross-attention through the same kernel (A/B: slower),
- * -1 = back to the default / CE_ATTN_V2. */
+ * (experimental), 0 = single-tile kernel, -1 = back to the default / CE_ATTN_V2. */
 int ce_debug_attention_kernel(int version);
 
 /* Cross-attention with TWO key/value sources in one launch: out = bf16(SDPA(q,k,v)) + bf16(SDPA(q,k2,v2)) — the text and

@@ -57,7 +57,7 @@ def test_no_cpu_fallback():
     assert lib.ce_unipc_step(ctypes.byref(args), None) == -3 and b"no CPU fallback" in lib.ce_last_error()
     args.p_order = 3
     assert lib.ce_unipc_step(ctypes.byref(args), None) == -1
-    assert lib.ce_debug_attention_kernel(9) == -1 and lib.ce_debug_attention_kernel(-1) == 0
+    assert lib.ce_debug_attention_kernel(7) == -1 and lib.ce_debug_attention_kernel(-1) == 0
 
 
 def test_rope_table_host_matches_oracle():

@@ -270,11 +270,11 @@ def test_rmsnorm_rope(rows, H, rope):
 
 
 @gpu
-@pytest.mark.parametrize("Lq,Lk,Lk2,version", [(300, 512, 257, -1), (7200, 512, 257, -1), (130, 7, 300, -1), (300, 7, 300, 7), (513, 640, 129, 7),
-                                               (7200, 512, 257, 7)])
+@pytest.mark.parametrize("Lq,Lk,Lk2,version", [(300, 512, 257, -1), (7200, 512, 257, -1), (130, 7, 300, -1), (300, 7, 300, -1), (513, 640, 129, -1),
+                                               (300, 512, 257, 2)])
 def test_attention_dual_source(Lq, Lk, Lk2, version):
-    """text + image cross-attention in one launch == sum of two separate bf16 SDPAs (transformer_chronoedit.py:84-104).  Default:
-    attention.cu's two-group kernel; version 7: attention6.cu's two-source mode (the sources one after the other in a 256-query CTA)."""
+    """text + image cross-attention in one launch == sum of two separate bf16 SDPAs (transformer_chronoedit.py:84-104): attention.cu's
+    two-group kernel whatever serves the self-attention."""
     L = _lib()
     lib = L.lib()
     L.check(lib.ce_debug_attention_kernel(version))
