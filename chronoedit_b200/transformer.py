@@ -208,6 +208,15 @@ class ChronoEditTransformer3DModel(nn.Module):
         self._workspaces = {}
         return super()._apply(fn, *a, **k)
 
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        # new weights under the same prompt tensors: the cached cross-attention K/V and any captured graph are stale; with
+        # assign=True the parameters are new tensors, so the fused device buffers must be rebuilt as well
+        self._ctx_cache = []
+        self._graphs = {}
+        if assign:
+            self._packed = False
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None):

@@ -148,3 +148,20 @@ def test_wan_to_diffusers_module_map_matches_reference_converter():
     assert '"blocks.0.attn2.add_v_proj.weight": "blocks.0.cross_attn.v_img.weight"' in src
     for wan, dif in ce.ChronoEditTransformer3DModel._WAN_TO_DIFFUSERS_GLOBAL.items():
         assert f'"{dif}.weight": "{wan}.weight"' in src, (wan, dif)
+
+
+def test_new_weights_drop_the_context_cache():
+    """The step-invariant context cache is keyed on the conditioning tensors only, so anything that changes the weights has to empty
+    it: load_state_dict (also mid-session), fuse_lora (tested above through its effect on the weights), .to()."""
+    import chronoedit_b200 as ce
+
+    m = ce.ChronoEditTransformer3DModel(num_attention_heads=2, in_channels=36, ffn_dim=256, num_layers=1, image_dim=1280, added_kv_proj_dim=256,
+                                        text_dim=64, cache_context=True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m._ctx_cache = [dict(txt=None, img=None, txt_v=None, img_v=None, buf=None)]
+    m._graphs = {"k": object()}
+    m.load_state_dict(sd)
+    assert m._ctx_cache == [] and m._graphs == {}
+    m._ctx_cache = [dict(txt=None, img=None, txt_v=None, img_v=None, buf=None)]
+    m.to(torch.bfloat16)
+    assert m._ctx_cache == []
